@@ -1,0 +1,27 @@
+"""pytest configuration: registers the `gpu` marker and shared fixtures."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+  config.addinivalue_line(
+      'markers', 'gpu: test needs a CUDA device (run on the B200 box)')
+
+
+def load_golden(name):
+  return np.load(os.path.join(GOLDEN_DIR, name + '.npz'), allow_pickle=False)
+
+
+@pytest.fixture(scope='session')
+def golden():
+  return load_golden
