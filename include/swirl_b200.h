@@ -1,0 +1,242 @@
+/*
+ * swirl_b200.h -- C ABI of libswirl_b200.so: the B200-native (sm_100a) hot
+ * path of Swirl-FEM (matrix-free tensor-product operator apply, element <->
+ * global gather-scatter, fused PCG, shared-dof exchange).
+ *
+ * The reference (google-research/swirl-fem) is pure Python/JAX and has NO FFI
+ * of its own; each entry point below replaces one JAX-level function of the
+ * reference (cited as file:line relative to the reference root) and is what a
+ * `jax.ffi` custom call for that function would bind (see INTEGRATION.md and
+ * swirl_fem_b200/csrc/xla_ffi_shim.cc).
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, scalars; no torch / jax types.
+ *   - every array pointer is a DEVICE pointer owned by the caller unless the
+ *     parameter is documented as "host".  Nothing is freed by the library
+ *     except the handles it allocates (small host structs + O(N^2) device
+ *     tables for the 1-D matrices).
+ *   - work is enqueued on the caller's stream (`sfem_stream_t`, a
+ *     cudaStream_t); no host synchronisation except where stated.
+ *   - return value: 0 on success, negative `sfem_status` on error;
+ *     `sfem_last_error()` gives a thread-local message.
+ *   - dtype is the arithmetic type of the path: SFEM_F32 or SFEM_F64.
+ *   - tensor index convention follows the reference: coordinate 0 is the
+ *     SLOWEST axis of the element-local node ordering
+ *     (swirl_fem/core/interpolation.py:252, 285-286).
+ */
+#ifndef SWIRL_B200_H_
+#define SWIRL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* sfem_stream_t;
+
+enum sfem_dtype { SFEM_F32 = 0, SFEM_F64 = 1 };
+
+enum sfem_status {
+  SFEM_OK = 0,
+  SFEM_ERR_INVALID = -1,      /* bad argument / shape                        */
+  SFEM_ERR_UNSUPPORTED = -2,  /* combination not implemented (no fallback)   */
+  SFEM_ERR_CUDA = -3,         /* CUDA runtime error, see sfem_last_error()   */
+  SFEM_ERR_NCCL = -4
+};
+
+#define SFEM_SENTINEL (-1) /* swirl_fem/core/gather_scatter.py:118 */
+#define SFEM_MAX_1D 18     /* max nodes / quadrature points per axis         */
+
+const char* sfem_last_error(void);
+int sfem_version(void);
+/* Number of kernels launched by this library in this process (bench.py's
+ * `gpu_launches` claim). */
+int64_t sfem_launch_count(void);
+
+/* ------------------------------------------------------------------------ */
+/* K1 / K7 / K9: gather, scatter, exchange                                   */
+/* ------------------------------------------------------------------------ */
+
+/* out[i] = indices[i] == SENTINEL ? fill : u[indices[i]*stride + offset].
+ * Replaces gather_scatter.gather (swirl_fem/core/gather_scatter.py:121-127)
+ * and Mesh.gather (swirl_fem/core/mesh.py:155-160).  `out` is written with
+ * element stride `stride` too, so a (G,d) AoS field is gathered one component
+ * per call (the reference vmaps over the last axis, navier_stokes.py:210-212).
+ */
+int sfem_gather(int dtype, const void* u, const int32_t* indices,
+                int64_t count, double fill_value, int32_t stride,
+                int32_t offset, void* out, sfem_stream_t stream);
+
+/* out = zeros(num_nodes); out[indices[i]] += u_local[i] (SENTINEL skipped).
+ * Replaces gather_scatter.scatter (gather_scatter.py:130-133) / Mesh.scatter
+ * (mesh.py:165-168).  Atomic (REDG) accumulation; `out` is zeroed first. */
+int sfem_scatter_add(int dtype, const void* u_local, const int32_t* indices,
+                     int64_t count, int64_t num_nodes, int32_t stride,
+                     int32_t offset, void* out, sfem_stream_t stream);
+
+/* Deterministic scatter: a transposed (node -> local slots) CSR map built once
+ * on the device, then a warp-segmented gather-sum with no atomics.
+ * Workspace sizes are returned by sfem_scatter_plan_size(). */
+typedef struct sfem_scatter_plan sfem_scatter_plan;
+int sfem_scatter_plan_create(const int32_t* indices, int64_t count,
+                             int64_t num_nodes, sfem_scatter_plan** plan,
+                             sfem_stream_t stream);
+int sfem_scatter_plan_apply(const sfem_scatter_plan* plan, int dtype,
+                            const void* u_local, int32_t stride,
+                            int32_t offset, void* out, sfem_stream_t stream);
+void sfem_scatter_plan_destroy(sfem_scatter_plan* plan);
+
+/* Unpartitioned QQ^T (periodic dofs), gather_scatter.exchange
+ * (gather_scatter.py:189-261): u[gi] <- sum over the group `ui` of u[gi].
+ * `scratch` holds `num_unique` values of dtype.  In place on `u`. */
+int sfem_exchange(int dtype, void* u, const int32_t* gather_indices,
+                  const int32_t* unique_indices, int64_t count,
+                  int64_t num_unique, int32_t stride, int32_t offset,
+                  void* scratch, sfem_stream_t stream);
+
+/* Partitioned QQ^T building blocks (halo exchange; the wire step is NCCL /
+ * NVLink peer copies driven by the host layer):
+ * pack:   buf[i]  = u[send_idx[i]]
+ * unpack: u[recv_idx[i]] += buf[i]                                          */
+int sfem_halo_pack(int dtype, const void* u, const int32_t* idx, int64_t count,
+                   void* buf, sfem_stream_t stream);
+int sfem_halo_unpack_add(int dtype, void* u, const int32_t* idx, int64_t count,
+                         const void* buf, sfem_stream_t stream);
+
+/* ------------------------------------------------------------------------ */
+/* FE space: geometric factors, q-function evaluation, integration          */
+/* ------------------------------------------------------------------------ */
+
+typedef struct {
+  int32_t dim;            /* 1, 2, 3                                         */
+  int32_t n1d;            /* N: grid nodes per axis (order + 1)              */
+  int32_t q1d;            /* Q: quadrature points per axis                   */
+  int32_t dtype;          /* SFEM_F32 / SFEM_F64                             */
+  int32_t collocated;     /* 1: quadrature nodes == grid nodes (B = I)       */
+  int32_t reserved;
+  int64_t num_elements;   /* E                                               */
+  int64_t num_nodes;      /* G                                               */
+  const int32_t* elements;      /* device (E, N^dim) int32, SENTINEL allowed */
+  const void* node_coords;      /* device (G, dim), dtype                    */
+  const double* interp_1d;      /* host (Q, N): B[q][n] = l_n(x_q)           */
+  const double* interp_grad_1d; /* host (Q, N): B @ D                        */
+  const double* quad_weights_1d;/* host (Q)                                  */
+} sfem_space_desc;
+
+typedef struct sfem_space sfem_space;
+
+/* FiniteElementSpace.create (swirl_fem/core/fespace.py:306-348).  Outputs are
+ * caller-owned device arrays (any may be NULL):
+ *   invjacs (E, Q^d, d, d), jacdets (E, Q^d) [signed], quad_coords (E, Q^d, d).
+ * The handle keeps the descriptor, device copies of the 1-D matrices and the
+ * three output pointers (they must outlive the handle). */
+int sfem_space_create(const sfem_space_desc* desc, void* invjacs,
+                      void* jacdets, void* quad_coords, sfem_space** space,
+                      sfem_stream_t stream);
+void sfem_space_destroy(sfem_space* space);
+
+/* Scalar/VectorNodalQFunction[Grad]._evaluate (fespace.py:178-225).
+ * u_local: (E, N^d, ncomp) AoS.  kind 0: values -> out (E, Q^d, ncomp);
+ * kind 1: physical gradient -> out (E, Q^d, d, ncomp), out[..j,k] = d u_k/dx_j
+ * (for ncomp == 1 that is the reference's (E, Q^d, d)). */
+int sfem_space_eval(const sfem_space* space, const void* u_local,
+                    int32_t ncomp, int32_t kind, void* out,
+                    sfem_stream_t stream);
+
+/* FiniteElementSpace.integrate (fespace.py:381-403):
+ * *result = sum_{e,q} w[e,q] * jacdets[e,q] * W[q].  result: device fp64
+ * scalar (always double, zeroed by the call). */
+int sfem_space_integrate(const sfem_space* space, const void* w, void* result,
+                         sfem_stream_t stream);
+
+/* ------------------------------------------------------------------------ */
+/* Operator: y = mask . Z^T (lambda*Mass + mu*Stiffness) Z x                 */
+/* ------------------------------------------------------------------------ */
+
+typedef struct sfem_op sfem_op;
+
+/* Bytes needed for the packed geometric factors and the packed connectivity
+ * of an operator on `desc` (caller allocates both on the device). */
+int64_t sfem_op_geom_bytes(const sfem_space_desc* desc, int32_t with_mass);
+int64_t sfem_op_conn_bytes(const sfem_space_desc* desc);
+
+/* Builds the operator of FiniteElementSpace.local_covector
+ * (fespace.py:405-471) for the bilinear forms
+ *   lambda * u v + mu * grad u . grad v
+ * (mass `l` / stiffness `a`, swirl_fem/examples/poisson.py:133-137; Helmholtz
+ * H_, swirl_fem/navier_stokes/navier_stokes.py:431), fused with Mesh.gather,
+ * Mesh.scatter and the Dirichlet mask of poisson.py:119-130, 141-146.
+ *   dirichlet: device (G) uint8, 1 = constrained row (zeroed), or NULL.
+ *   geom / conn: caller-owned device buffers of the sizes above; filled here
+ *   (one-time setup kernels, K11) and kept by the handle.
+ *   with_mass: store W*detJ as well (needed when lambda != 0).              */
+int sfem_op_create(const sfem_space_desc* desc, const uint8_t* dirichlet,
+                   int32_t with_mass, void* geom, void* conn, sfem_op** op,
+                   sfem_stream_t stream);
+void sfem_op_destroy(sfem_op* op);
+
+/* y = mask . scatter(local_op(gather(x))).  x, y: (G, ncomp) AoS of dtype;
+ * y is fully overwritten.  If `dot_xy` != NULL it receives x . y (device fp64
+ * scalar, always double) computed in the kernel epilogue -- the p.Ap of
+ * cg.py:77.  */
+int sfem_op_apply(const sfem_op* op, double lambda, double mu, const void* x,
+                  void* y, int32_t ncomp, void* dot_xy, sfem_stream_t stream);
+
+/* Local (E-vector) form: y_local = local_covector(form, (u_local, v)).
+ * u_local, y_local: (E, N^d, ncomp). */
+int sfem_op_apply_local(const sfem_op* op, double lambda, double mu,
+                        const void* u_local, void* y_local, int32_t ncomp,
+                        sfem_stream_t stream);
+
+/* diag(mask . Z^T (lambda M + mu K) Z) (K12; Jacobi preconditioner).        */
+int sfem_op_diag(const sfem_op* op, double lambda, double mu, void* diag,
+                 sfem_stream_t stream);
+
+/* Selects the kernel family: 0 = auto (specialised collocated kernels where
+ * available), 1 = force the generic runtime-(N,Q) kernel.  For tests.       */
+int sfem_op_set_variant(sfem_op* op, int32_t variant);
+
+/* ------------------------------------------------------------------------ */
+/* CG (swirl_fem/linalg/cg.py:30-97)                                         */
+/* ------------------------------------------------------------------------ */
+
+typedef struct {
+  double tol;          /* relative tolerance (default 1e-5)                  */
+  double atol;         /* absolute tolerance                                 */
+  int64_t maxiter;     /* <= 0: 10 * size                                    */
+  int32_t precond;     /* 0: identity, 1: Jacobi (minv = 1/diag, 0 on mask)  */
+  int32_t check_every; /* host polls the device flag every k iterations      */
+  double lambda, mu;   /* operator coefficients                              */
+} sfem_cg_params;
+
+typedef struct {
+  double residual;        /* gamma = r . M r at exit (cg.py:96)              */
+  int64_t num_iterations;
+} sfem_cg_info;
+
+/* Bytes of device workspace sfem_cg needs for a system of `size` unknowns. */
+int64_t sfem_cg_workspace_bytes(int dtype, int64_t size);
+
+/* Solves A x = b with A = the operator (ncomp components).  x holds x0 on
+ * entry (pass zeros for the reference default) and the solution on exit.
+ * minv: device (G*ncomp) inverse diagonal for precond == 1, else NULL.
+ * Synchronises the stream only to read the convergence flag every
+ * `check_every` iterations and at exit. */
+int sfem_cg(const sfem_op* op, const void* b, void* x, int32_t ncomp,
+            const void* minv, const sfem_cg_params* params, void* workspace,
+            sfem_cg_info* info, sfem_stream_t stream);
+
+/* Fused vector kernels for the generic (callable-A) CG path.  All device. */
+/* y = a*x + b*y */
+int sfem_axpby(int dtype, int64_t n, double a, const void* x, double b,
+               void* y, sfem_stream_t stream);
+/* *result = x . y   (result: device fp64 scalar, always double) */
+int sfem_dot(int dtype, int64_t n, const void* x, const void* y, void* result,
+             sfem_stream_t stream);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* SWIRL_B200_H_ */

@@ -1,0 +1,353 @@
+"""ctypes binding of libswirl_b200.so (the C ABI in include/swirl_b200.h).
+
+PyTorch is used here only as plumbing: device memory (`torch.empty(...,
+device='cuda')`), the current CUDA stream and dtype bookkeeping.  Every
+compute call goes through the C ABI into hand-written sm_100a kernels.  There
+is NO CPU fallback: if the shared library is missing, or a tensor is not on a
+CUDA device, the call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libswirl_b200.so')
+CSRC_DIR = os.path.join(_HERE, 'csrc')
+
+SFEM_F32, SFEM_F64 = 0, 1
+SENTINEL = -1
+MAX_1D = 18
+
+_c_i32 = ctypes.c_int32
+_c_i64 = ctypes.c_int64
+_c_f64 = ctypes.c_double
+_c_ptr = ctypes.c_void_p
+
+
+class SpaceDesc(ctypes.Structure):
+  """`sfem_space_desc` (include/swirl_b200.h)."""
+  _fields_ = [
+      ('dim', _c_i32), ('n1d', _c_i32), ('q1d', _c_i32), ('dtype', _c_i32),
+      ('collocated', _c_i32), ('reserved', _c_i32),
+      ('num_elements', _c_i64), ('num_nodes', _c_i64),
+      ('elements', _c_ptr), ('node_coords', _c_ptr),
+      ('interp_1d', _c_ptr), ('interp_grad_1d', _c_ptr),
+      ('quad_weights_1d', _c_ptr),
+  ]
+
+
+class CgParams(ctypes.Structure):
+  """`sfem_cg_params`."""
+  _fields_ = [
+      ('tol', _c_f64), ('atol', _c_f64), ('maxiter', _c_i64),
+      ('precond', _c_i32), ('check_every', _c_i32),
+      ('lam', _c_f64), ('mu', _c_f64),
+  ]
+
+
+class CgInfo(ctypes.Structure):
+  """`sfem_cg_info`."""
+  _fields_ = [('residual', _c_f64), ('num_iterations', _c_i64)]
+
+
+# name -> (restype, argtypes): every symbol include/swirl_b200.h declares.
+SIGNATURES = {
+    'sfem_last_error': (ctypes.c_char_p, []),
+    'sfem_version': (ctypes.c_int, []),
+    'sfem_launch_count': (_c_i64, []),
+    'sfem_gather': (ctypes.c_int, [ctypes.c_int, _c_ptr, _c_ptr, _c_i64, _c_f64,
+                                   _c_i32, _c_i32, _c_ptr, _c_ptr]),
+    'sfem_scatter_add': (ctypes.c_int, [ctypes.c_int, _c_ptr, _c_ptr, _c_i64,
+                                        _c_i64, _c_i32, _c_i32, _c_ptr,
+                                        _c_ptr]),
+    'sfem_scatter_plan_create': (ctypes.c_int, [_c_ptr, _c_i64, _c_i64,
+                                                ctypes.POINTER(_c_ptr),
+                                                _c_ptr]),
+    'sfem_scatter_plan_apply': (ctypes.c_int, [_c_ptr, ctypes.c_int, _c_ptr,
+                                               _c_i32, _c_i32, _c_ptr, _c_ptr]),
+    'sfem_scatter_plan_destroy': (None, [_c_ptr]),
+    'sfem_exchange': (ctypes.c_int, [ctypes.c_int, _c_ptr, _c_ptr, _c_ptr,
+                                     _c_i64, _c_i64, _c_i32, _c_i32, _c_ptr,
+                                     _c_ptr]),
+    'sfem_halo_pack': (ctypes.c_int, [ctypes.c_int, _c_ptr, _c_ptr, _c_i64,
+                                      _c_ptr, _c_ptr]),
+    'sfem_halo_unpack_add': (ctypes.c_int, [ctypes.c_int, _c_ptr, _c_ptr,
+                                            _c_i64, _c_ptr, _c_ptr]),
+    'sfem_space_create': (ctypes.c_int, [ctypes.POINTER(SpaceDesc), _c_ptr,
+                                         _c_ptr, _c_ptr,
+                                         ctypes.POINTER(_c_ptr), _c_ptr]),
+    'sfem_space_destroy': (None, [_c_ptr]),
+    'sfem_space_eval': (ctypes.c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr,
+                                       _c_ptr]),
+    'sfem_space_integrate': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+    'sfem_op_geom_bytes': (_c_i64, [ctypes.POINTER(SpaceDesc), _c_i32]),
+    'sfem_op_conn_bytes': (_c_i64, [ctypes.POINTER(SpaceDesc)]),
+    'sfem_op_create': (ctypes.c_int, [ctypes.POINTER(SpaceDesc), _c_ptr,
+                                      _c_i32, _c_ptr, _c_ptr,
+                                      ctypes.POINTER(_c_ptr), _c_ptr]),
+    'sfem_op_destroy': (None, [_c_ptr]),
+    'sfem_op_apply': (ctypes.c_int, [_c_ptr, _c_f64, _c_f64, _c_ptr, _c_ptr,
+                                     _c_i32, _c_ptr, _c_ptr]),
+    'sfem_op_apply_local': (ctypes.c_int, [_c_ptr, _c_f64, _c_f64, _c_ptr,
+                                           _c_ptr, _c_i32, _c_ptr]),
+    'sfem_op_diag': (ctypes.c_int, [_c_ptr, _c_f64, _c_f64, _c_ptr, _c_ptr]),
+    'sfem_op_set_variant': (ctypes.c_int, [_c_ptr, _c_i32]),
+    'sfem_cg_workspace_bytes': (_c_i64, [ctypes.c_int, _c_i64]),
+    'sfem_cg': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr,
+                               ctypes.POINTER(CgParams), _c_ptr,
+                               ctypes.POINTER(CgInfo), _c_ptr]),
+    'sfem_axpby': (ctypes.c_int, [ctypes.c_int, _c_i64, _c_f64, _c_ptr, _c_f64,
+                                  _c_ptr, _c_ptr]),
+    'sfem_dot': (ctypes.c_int, [ctypes.c_int, _c_i64, _c_ptr, _c_ptr, _c_ptr,
+                                _c_ptr]),
+}
+
+_lib = None
+
+
+class SwirlB200Error(RuntimeError):
+  pass
+
+
+def build(verbose: bool = False) -> str:
+  """Compiles the CUDA sources in-tree for sm_100a (nvcc, `make -j`)."""
+  jobs = str(max(1, min(8, os.cpu_count() or 1)))
+  proc = subprocess.run(['make', '-j', jobs, '-C', CSRC_DIR],
+                        capture_output=True, text=True)
+  if verbose or proc.returncode != 0:
+    print(proc.stdout)
+    print(proc.stderr)
+  if proc.returncode != 0:
+    raise SwirlB200Error('building libswirl_b200.so failed')
+  return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+  """Loads the shared library (never falls back to anything else)."""
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      raise SwirlB200Error(
+          f'{LIB_PATH} not found: build it with `python -c "import '
+          '__graft_entry__ as g; g.build()"` (needs nvcc).  There is no CPU '
+          'fallback.')
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+      fn = getattr(handle, name)  # AttributeError if a symbol is missing
+      fn.restype = restype
+      fn.argtypes = argtypes
+    _lib = handle
+  return _lib
+
+
+def _check(rc: int, what: str):
+  if rc != 0:
+    msg = lib().sfem_last_error().decode('utf-8', 'replace')
+    if rc == -2:
+      raise NotImplementedError(f'{what}: {msg}')
+    if rc == -1:
+      raise ValueError(f'{what}: {msg}')
+    raise SwirlB200Error(f'{what} failed ({rc}): {msg}')
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+  if dtype == torch.float64:
+    return SFEM_F64
+  if dtype == torch.float32:
+    return SFEM_F32
+  raise TypeError(f'swirl_fem_b200 computes in float32 or float64, got {dtype}')
+
+
+def require_cuda(*tensors):
+  for t in tensors:
+    if t is not None and not t.is_cuda:
+      raise SwirlB200Error(
+          'swirl_fem_b200 has no CPU path: tensors must live on a CUDA device '
+          f'(got device={t.device})')
+
+
+def stream_ptr(device=None) -> int:
+  return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+  return None if t is None else t.data_ptr()
+
+
+def launch_count() -> int:
+  return int(lib().sfem_launch_count())
+
+
+# ----------------------------------------------------------------------------
+# gather / scatter / exchange
+# ----------------------------------------------------------------------------
+
+
+def _as_index(indices: torch.Tensor) -> torch.Tensor:
+  if indices.dtype != torch.int32:
+    indices = indices.to(torch.int32)
+  return indices.contiguous()
+
+
+def gather(u: torch.Tensor, indices: torch.Tensor, fill_value=SENTINEL):
+  require_cuda(u, indices)
+  u = u.contiguous()
+  idx = _as_index(indices)
+  out = torch.empty(idx.shape, dtype=u.dtype, device=u.device)
+  with torch.cuda.device(u.device):
+    _check(lib().sfem_gather(dtype_code(u.dtype), ptr(u), ptr(idx),
+                             idx.numel(), float(fill_value), 1, 0, ptr(out),
+                             stream_ptr(u.device)), 'sfem_gather')
+  return out
+
+
+def scatter(u_local: torch.Tensor, indices: torch.Tensor, num_nodes: int):
+  require_cuda(u_local, indices)
+  u_local = u_local.contiguous()
+  idx = _as_index(indices)
+  out = torch.empty(num_nodes, dtype=u_local.dtype, device=u_local.device)
+  with torch.cuda.device(u_local.device):
+    _check(lib().sfem_scatter_add(dtype_code(u_local.dtype), ptr(u_local),
+                                  ptr(idx), idx.numel(), num_nodes, 1, 0,
+                                  ptr(out), stream_ptr(u_local.device)),
+           'sfem_scatter_add')
+  return out
+
+
+class ScatterPlan:
+  """Deterministic (atomic-free) scatter: sorted map + warp-segmented sums."""
+
+  def __init__(self, indices: torch.Tensor, num_nodes: int):
+    require_cuda(indices)
+    self.indices = _as_index(indices)
+    self.num_nodes = int(num_nodes)
+    handle = _c_ptr()
+    with torch.cuda.device(self.indices.device):
+      _check(lib().sfem_scatter_plan_create(
+          ptr(self.indices), self.indices.numel(), self.num_nodes,
+          ctypes.byref(handle), stream_ptr(self.indices.device)),
+             'sfem_scatter_plan_create')
+    self._handle = handle
+
+  def __call__(self, u_local: torch.Tensor) -> torch.Tensor:
+    require_cuda(u_local)
+    if u_local.numel() != self.indices.numel():
+      raise ValueError('u_local does not match the plan')
+    u_local = u_local.contiguous()
+    out = torch.empty(self.num_nodes, dtype=u_local.dtype,
+                      device=u_local.device)
+    with torch.cuda.device(u_local.device):
+      _check(lib().sfem_scatter_plan_apply(
+          self._handle, dtype_code(u_local.dtype), ptr(u_local), 1, 0,
+          ptr(out), stream_ptr(u_local.device)), 'sfem_scatter_plan_apply')
+    return out
+
+  def __del__(self):
+    h = getattr(self, '_handle', None)
+    if h and _lib is not None:
+      _lib.sfem_scatter_plan_destroy(h)
+      self._handle = None
+
+
+def exchange(u: torch.Tensor, gather_indices: torch.Tensor,
+             unique_indices: torch.Tensor | None):
+  require_cuda(u, gather_indices, unique_indices)
+  out = u.contiguous().clone()
+  gi = _as_index(gather_indices)
+  ui = None if unique_indices is None else _as_index(unique_indices)
+  count = gi.numel()
+  if count == 0:
+    return out
+  num_unique = count if ui is None else int(ui.max().item()) + 1
+  scratch = torch.empty(num_unique, dtype=u.dtype, device=u.device)
+  with torch.cuda.device(u.device):
+    _check(lib().sfem_exchange(dtype_code(u.dtype), ptr(out), ptr(gi), ptr(ui),
+                               count, num_unique, 1, 0, ptr(scratch),
+                               stream_ptr(u.device)), 'sfem_exchange')
+  return out
+
+
+def halo_pack(u, idx, buf):
+  require_cuda(u, idx, buf)
+  with torch.cuda.device(u.device):
+    _check(lib().sfem_halo_pack(dtype_code(u.dtype), ptr(u), ptr(idx),
+                                idx.numel(), ptr(buf), stream_ptr(u.device)),
+           'sfem_halo_pack')
+
+
+def halo_unpack_add(u, idx, buf):
+  require_cuda(u, idx, buf)
+  with torch.cuda.device(u.device):
+    _check(lib().sfem_halo_unpack_add(dtype_code(u.dtype), ptr(u), ptr(idx),
+                                      idx.numel(), ptr(buf),
+                                      stream_ptr(u.device)),
+           'sfem_halo_unpack_add')
+
+
+# ----------------------------------------------------------------------------
+# vector kernels
+# ----------------------------------------------------------------------------
+
+
+def axpby(a: float, x: torch.Tensor, b: float, y: torch.Tensor):
+  """y <- a*x + b*y (in place on y)."""
+  require_cuda(x, y)
+  assert x.dtype == y.dtype and x.numel() == y.numel()
+  assert x.is_contiguous() and y.is_contiguous()
+  with torch.cuda.device(x.device):
+    _check(lib().sfem_axpby(dtype_code(x.dtype), x.numel(), float(a), ptr(x),
+                            float(b), ptr(y), stream_ptr(x.device)),
+           'sfem_axpby')
+  return y
+
+
+def dot(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+  """Returns x . y as a 0-d float64 device tensor."""
+  require_cuda(x, y)
+  assert x.dtype == y.dtype and x.numel() == y.numel()
+  x = x.contiguous()
+  y = y.contiguous()
+  out = torch.empty((), dtype=torch.float64, device=x.device)
+  with torch.cuda.device(x.device):
+    _check(lib().sfem_dot(dtype_code(x.dtype), x.numel(), ptr(x), ptr(y),
+                          ptr(out), stream_ptr(x.device)), 'sfem_dot')
+  return out
+
+
+# ----------------------------------------------------------------------------
+# descriptor helper
+# ----------------------------------------------------------------------------
+
+
+class Desc:
+  """Keeps the host arrays referenced by a `sfem_space_desc` alive."""
+
+  def __init__(self, *, dim, n1d, q1d, dtype, collocated, elements,
+               node_coords, interp_1d, interp_grad_1d, quad_weights_1d):
+    require_cuda(elements, node_coords)
+    if n1d > MAX_1D or q1d > MAX_1D:
+      raise NotImplementedError(
+          f'at most {MAX_1D} nodes / quadrature points per axis')
+    self.elements = _as_index(elements)
+    self.node_coords = node_coords.to(dtype).contiguous()
+    self.b = np.ascontiguousarray(interp_1d, dtype=np.float64)
+    self.bd = np.ascontiguousarray(interp_grad_1d, dtype=np.float64)
+    self.w = np.ascontiguousarray(quad_weights_1d, dtype=np.float64)
+    assert self.b.shape == (q1d, n1d) and self.bd.shape == (q1d, n1d)
+    assert self.w.shape == (q1d,)
+    self.c = SpaceDesc(
+        dim=dim, n1d=n1d, q1d=q1d, dtype=dtype_code(dtype),
+        collocated=int(bool(collocated)), reserved=0,
+        num_elements=self.elements.shape[0],
+        num_nodes=self.node_coords.shape[0],
+        elements=ptr(self.elements), node_coords=ptr(self.node_coords),
+        interp_1d=self.b.ctypes.data, interp_grad_1d=self.bd.ctypes.data,
+        quad_weights_1d=self.w.ctypes.data)
+    self.dtype = dtype
+    self.device = self.node_coords.device

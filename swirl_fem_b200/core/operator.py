@@ -1,0 +1,155 @@
+"""Fused matrix-free operator  y = mask . Z^T (lam*Mass + mu*Stiffness) Z x.
+
+This is the B200 replacement for the reference's operator lambdas
+  `A(u) = with_bc(mesh.scatter(fespace.local_covector(a, (gather(u), v))))`
+(`swirl_fem/examples/poisson.py:119-146`), `StokesSEM.A` / `H_`
+(`swirl_fem/navier_stokes/navier_stokes.py:304-307, 431`): one CUDA kernel does
+gather -> sum-factorised local operator -> scatter -> Dirichlet mask, and
+(optionally) the `p . Ap` dot product of CG in its epilogue.
+
+The handle owns two device buffers (torch tensors, caller-visible):
+  `geom`  (E, g, Q^d): symmetric geometric factors W detJ J^-T J^-1 (+ W detJ),
+  `conn`  (E, N^d) int32: connectivity with the "single occurrence" and
+          "Dirichlet" flags folded into the two top bits.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from swirl_fem_b200 import _lib
+
+
+class FusedOperator:
+  """`sfem_op` handle bound to a `FiniteElementSpace`."""
+
+  def __init__(self, fespace, dirichlet_mask=None, with_mass: bool = True):
+    self.fespace = fespace
+    mesh = fespace.mesh
+    interp = fespace.interpolator
+    b, bd = interp.matrices_1d()
+    self.dtype = fespace.dtype
+    self.desc = _lib.Desc(
+        dim=mesh.ndim, n1d=mesh.gridpoints_1d.num_points,
+        q1d=fespace.quadrature.num_points, dtype=self.dtype,
+        collocated=interp.collocated, elements=mesh.elements,
+        node_coords=mesh.node_coords, interp_1d=b, interp_grad_1d=bd,
+        quad_weights_1d=fespace.quadrature.weights)
+    dev = mesh.device
+    self.with_mass = bool(with_mass)
+    if dirichlet_mask is not None:
+      dm = dirichlet_mask
+      if not isinstance(dm, torch.Tensor):
+        dm = torch.as_tensor(np.asarray(dm))
+      dm = (dm.to(dev) != 0).to(torch.uint8).contiguous()
+      if tuple(dm.shape) != (mesh.num_nodes,):
+        raise ValueError('dirichlet_mask must have shape (num_nodes,)')
+      self.dirichlet = dm
+    else:
+      self.dirichlet = None
+    lib = _lib.lib()
+    gbytes = lib.sfem_op_geom_bytes(ctypes.byref(self.desc.c),
+                                    int(self.with_mass))
+    cbytes = lib.sfem_op_conn_bytes(ctypes.byref(self.desc.c))
+    esz = torch.empty((), dtype=self.dtype).element_size()
+    self.geom = torch.empty(max(gbytes // esz, 1), dtype=self.dtype, device=dev)
+    self.conn = torch.empty(max(cbytes // 4, 1), dtype=torch.int32, device=dev)
+    handle = ctypes.c_void_p()
+    with torch.cuda.device(dev):
+      _lib._check(lib.sfem_op_create(
+          ctypes.byref(self.desc.c), _lib.ptr(self.dirichlet),
+          int(self.with_mass), _lib.ptr(self.geom), _lib.ptr(self.conn),
+          ctypes.byref(handle), _lib.stream_ptr(dev)), 'sfem_op_create')
+    self.handle = handle
+    self.num_nodes = mesh.num_nodes
+    self.ndim = mesh.ndim
+
+  def __del__(self):
+    h = getattr(self, 'handle', None)
+    if h and _lib._lib is not None:
+      _lib._lib.sfem_op_destroy(h)
+      self.handle = None
+
+  def set_variant(self, variant: int):
+    """0: auto (specialised collocated kernels), 1: generic kernel (tests)."""
+    _lib._check(_lib.lib().sfem_op_set_variant(self.handle, int(variant)),
+                'sfem_op_set_variant')
+
+  def _ncomp(self, x: torch.Tensor) -> int:
+    if x.dim() == 1:
+      return 1
+    if x.dim() == 2:
+      return x.shape[1]
+    raise ValueError(f'expected (G,) or (G, ncomp), got {tuple(x.shape)}')
+
+  def apply(self, x: torch.Tensor, lam: float = 0.0, mu: float = 1.0,
+            out: torch.Tensor | None = None, dot_out: torch.Tensor | None = None):
+    """y = mask . scatter(local(gather(x))).  `dot_out`: 0-d float64 for x.y."""
+    _lib.require_cuda(x)
+    if x.shape[0] != self.num_nodes:
+      raise ValueError(
+          f'Expected leading dimension {self.num_nodes}, got {tuple(x.shape)}')
+    x = x.to(self.dtype).contiguous()
+    y = torch.empty_like(x) if out is None else out
+    assert y.is_contiguous() and y.dtype == x.dtype and y.shape == x.shape
+    with torch.cuda.device(x.device):
+      _lib._check(_lib.lib().sfem_op_apply(
+          self.handle, float(lam), float(mu), _lib.ptr(x), _lib.ptr(y),
+          self._ncomp(x), _lib.ptr(dot_out), _lib.stream_ptr(x.device)),
+                  'sfem_op_apply')
+    return y
+
+  def apply_local(self, u_local: torch.Tensor, lam: float = 0.0,
+                  mu: float = 1.0, ncomp: int = 1) -> torch.Tensor:
+    """E-vector form: `(E, n[, ncomp]) -> (E, n[, ncomp])`."""
+    _lib.require_cuda(u_local)
+    u_local = u_local.to(self.dtype).contiguous()
+    y = torch.empty_like(u_local)
+    with torch.cuda.device(u_local.device):
+      _lib._check(_lib.lib().sfem_op_apply_local(
+          self.handle, float(lam), float(mu), _lib.ptr(u_local), _lib.ptr(y),
+          int(ncomp), _lib.stream_ptr(u_local.device)), 'sfem_op_apply_local')
+    return y
+
+  def diag(self, lam: float = 0.0, mu: float = 1.0) -> torch.Tensor:
+    """diag(mask . Z^T (lam M + mu K) Z): the Jacobi preconditioner's input."""
+    dev = self.fespace.mesh.device
+    d = torch.empty(self.num_nodes, dtype=self.dtype, device=dev)
+    with torch.cuda.device(dev):
+      _lib._check(_lib.lib().sfem_op_diag(
+          self.handle, float(lam), float(mu), _lib.ptr(d),
+          _lib.stream_ptr(dev)), 'sfem_op_diag')
+    return d
+
+  def jacobi_minv(self, lam: float = 0.0, mu: float = 1.0) -> torch.Tensor:
+    """`M(r) = mask . r / diag(A)` as an inverse-diagonal vector (0 on mask)."""
+    d = self.diag(lam, mu)
+    return torch.where(d != 0, 1.0 / d, torch.zeros_like(d))
+
+  def bind(self, lam: float = 0.0, mu: float = 1.0):
+    """Returns the callable `A(u)` for these coefficients (for `linalg.cg`)."""
+    return BoundOperator(self, lam, mu)
+
+
+class BoundOperator:
+  """`A(u)` with fixed (lam, mu); recognised by `linalg.cg.cg` (fused path)."""
+
+  def __init__(self, op: FusedOperator, lam: float, mu: float):
+    self.op, self.lam, self.mu = op, float(lam), float(mu)
+
+  def __call__(self, u: torch.Tensor) -> torch.Tensor:
+    return self.op.apply(u, lam=self.lam, mu=self.mu)
+
+
+class JacobiPreconditioner:
+  """`M(r) = minv * r`; recognised by `linalg.cg.cg` (fused path)."""
+
+  def __init__(self, minv: torch.Tensor):
+    self.minv = minv.contiguous()
+
+  def __call__(self, r: torch.Tensor) -> torch.Tensor:
+    m = self.minv
+    return r * (m if r.dim() == 1 else m.reshape(r.shape[0], -1))

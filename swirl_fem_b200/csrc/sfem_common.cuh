@@ -1,0 +1,155 @@
+// Shared device/host helpers for libswirl_b200 (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <string>
+
+#include "../../include/swirl_b200.h"
+
+namespace sfem {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const std::string& msg);
+extern std::atomic<int64_t> g_launch_count;
+
+#define SFEM_CUDA_CHECK(expr)                                                 \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess) {                                                  \
+      ::sfem::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));  \
+      return SFEM_ERR_CUDA;                                                   \
+    }                                                                         \
+  } while (0)
+
+#define SFEM_LAUNCH_CHECK()                                                   \
+  do {                                                                        \
+    ::sfem::g_launch_count.fetch_add(1, std::memory_order_relaxed);           \
+    cudaError_t _e = cudaGetLastError();                                      \
+    if (_e != cudaSuccess) {                                                  \
+      ::sfem::set_error(std::string("kernel launch: ") +                      \
+                        cudaGetErrorString(_e));                              \
+      return SFEM_ERR_CUDA;                                                   \
+    }                                                                         \
+  } while (0)
+
+#define SFEM_REQUIRE(cond, msg)                                               \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      ::sfem::set_error(std::string("invalid argument: ") + (msg));           \
+      return SFEM_ERR_INVALID;                                                \
+    }                                                                         \
+  } while (0)
+
+inline int num_sms() {
+  static int sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess)
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  return sms;
+}
+
+// ---- packed connectivity ------------------------------------------------------
+// One int32 per element-local node.  Low 30 bits: global node id.  Bit 31:
+// the node occurs exactly once in `elements` (plain store instead of RED).
+// Bit 30: Dirichlet row (result is 0).  A SENTINEL slot is encoded as
+// id = 0 with both flags set and never read or written.
+constexpr uint32_t kConnIdMask = 0x3fffffffu;
+constexpr uint32_t kConnSingle = 0x80000000u;
+constexpr uint32_t kConnDirichlet = 0x40000000u;
+constexpr uint32_t kConnSentinel = 0xffffffffu;
+
+// ---- small device helpers -----------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void red_add(T* addr, T v) {
+  atomicAdd(addr, v);  // result unused -> RED.E.ADD.F32/F64 in SASS
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum (any blockDim multiple of 32, <= 1024).  Result valid in
+// thread 0.  `smem` needs 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* smem) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (nthreads + 31) >> 5;
+    v = lane < nw ? smem[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  __syncthreads();
+  return v;
+}
+
+// streaming (read-once) loads: keep them out of L1
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T* p) {
+  return __ldcs(p);
+}
+
+// symmetric index of (i,k), i<=k, in the packed d(d+1)/2 layout
+__host__ __device__ constexpr int sym_index(int dim, int i, int k) {
+  return dim == 1 ? 0
+         : dim == 2 ? (i == 0 ? k : 2)
+                    : (i == 0 ? k : (i == 1 ? 2 + k : 5));
+}
+
+// ---- handles --------------------------------------------------------------------
+struct SpaceBase {
+  sfem_space_desc desc;
+  int n;  // N^dim
+  int q;  // Q^dim
+  // device copies of the 1-D tables in both precisions
+  double* d_tables64 = nullptr;  // [B | BD | W] (Q*N, Q*N, Q)
+  float* d_tables32 = nullptr;
+  double h_B[SFEM_MAX_1D * SFEM_MAX_1D];
+  double h_BD[SFEM_MAX_1D * SFEM_MAX_1D];
+  double h_W[SFEM_MAX_1D];
+};
+
+int space_base_init(SpaceBase* s, const sfem_space_desc* desc);
+void space_base_free(SpaceBase* s);
+
+template <typename T>
+inline const T* tables(const SpaceBase& s);
+template <>
+inline const double* tables<double>(const SpaceBase& s) {
+  return s.d_tables64;
+}
+template <>
+inline const float* tables<float>(const SpaceBase& s) {
+  return s.d_tables32;
+}
+
+}  // namespace sfem
+
+struct sfem_space {
+  sfem::SpaceBase base;
+  void* invjacs;
+  void* jacdets;
+  void* quad_coords;
+};
+
+struct sfem_op {
+  sfem::SpaceBase base;
+  const uint8_t* dirichlet;
+  int with_mass;
+  int ngeom;        // d(d+1)/2 (+1 with mass)
+  void* geom;       // (E, ngeom, Q^d) dtype
+  uint32_t* conn;   // (E, N^d) packed connectivity
+  int64_t n_zero;   // y[0 .. n_zero) must be zeroed before an apply
+  int variant;      // 0 auto, 1 generic
+};

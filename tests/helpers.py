@@ -1,0 +1,50 @@
+"""Shared builders for the parity tests (host-side, numpy)."""
+
+import numpy as np
+
+from swirl_fem_b200.common.premesh_commons import unit_cube_mesh
+from swirl_fem_b200.core.interpolation import Nodes1D
+from swirl_fem_b200.core.interpolation import NodeType
+from swirl_fem_b200.core.mesh_refiner import refine_premesh
+from swirl_fem_b200.core.premesh import Premesh
+
+GLL = NodeType.GAUSS_LOBATTO_LEGENDRE
+GL = NodeType.GAUSS_LEGENDRE
+TNAME = {GLL: 'gauss_lobatto_legendre', GL: 'gauss_legendre',
+         NodeType.NEWTON_COTES: 'newton_cotes'}
+
+
+def deform(x):
+  """Smooth non-affine map of [-1,1]^d keeping detJ > 0."""
+  x = np.asarray(x, dtype=np.float64)
+  ndim = x.shape[-1]
+  perm = np.roll(np.arange(ndim), 1) if ndim > 1 else np.arange(ndim)
+  return x + 0.08 * np.sin(np.pi * x[:, perm] + 0.3) * (1 - 0.5 * x ** 2)
+
+
+def shuffled(premesh: Premesh, seed: int) -> Premesh:
+  """Random element order + per-element axis permutation / flips."""
+  rng = np.random.default_rng(seed)
+  ndim = premesh.ndim
+  elements = np.array(premesh.elements)[rng.permutation(premesh.num_elements)]
+  out = []
+  for el in elements:
+    nd = el.reshape([2] * ndim).transpose(rng.permutation(ndim))
+    flips = [ax for ax in range(ndim) if rng.integers(2)]
+    nd = np.flip(nd, flips) if flips else nd
+    out.append(nd.reshape(-1))
+  return Premesh.create(node_coords=premesh.node_coords,
+                        elements=np.array(out, dtype=np.int32),
+                        physical_groups=premesh.physical_groups,
+                        periodic_links=premesh.periodic_links)
+
+
+def deformed_premesh(ndim, ne, n1d, seed=None, periodic_dims=(), curved=True):
+  """Refined GLL premesh on [-1,1]^ndim with deformed (curved) elements."""
+  pm = unit_cube_mesh(ne, ndim=ndim, a=-1., b=1., periodic_dims=periodic_dims)
+  if seed is not None:
+    pm = shuffled(pm, seed)
+  refined = refine_premesh(pm, Nodes1D.create(n1d, GLL))
+  if curved and not periodic_dims:
+    refined = refined.replace(node_coords=deform(refined.node_coords))
+  return refined

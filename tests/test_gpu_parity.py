@@ -1,0 +1,552 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle / goldens.
+
+Tolerances (BASELINE.json north_star): connectivity and gather/scatter
+indexing bit-exact; operator apply 1e-12 relative in fp64, 1e-5 in fp32; CG
+iteration counts within +-1.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dense
+from tests import helpers
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+GLL, GL = helpers.GLL, helpers.GL
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _need_cuda():
+  if not torch.cuda.is_available():
+    pytest.skip('needs a CUDA device')
+  from swirl_fem_b200 import _lib
+  _lib.lib()  # fail loudly if the extension is missing
+
+
+def dev(x, dtype=None):
+  t = torch.as_tensor(np.ascontiguousarray(x)).cuda()
+  return t if dtype is None else t.to(dtype)
+
+
+def rel_err(a, b):
+  a = np.asarray(a, dtype=np.float64)
+  b = np.asarray(b, dtype=np.float64)
+  return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+TOL = {torch.float64: 1e-12, torch.float32: 1e-5}
+
+
+# ----------------------------------------------------------------------------
+# gather / scatter / exchange
+# ----------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+def test_gather_scatter_bit_exact_indexing(dtype):
+  from swirl_fem_b200.core import gather_scatter as gs
+  rng = np.random.default_rng(0)
+  num_nodes = 1000
+  idx = rng.integers(0, num_nodes, size=(257, 27)).astype(np.int32)
+  idx[rng.random(idx.shape) < 0.05] = -1  # ragged: SENTINEL slots
+  u = rng.standard_normal(num_nodes)
+  npd = np.float64 if dtype == torch.float64 else np.float32
+  got = gs.gather(dev(u, dtype), dev(idx), fill_value=0.).cpu().numpy()
+  np.testing.assert_array_equal(got, dense.gather(u.astype(npd), idx, 0.))
+  got = gs.gather(dev(u, dtype), dev(idx)).cpu().numpy()  # default fill = -1
+  np.testing.assert_array_equal(got, dense.gather(u.astype(npd), idx, -1))
+  ul = rng.standard_normal(idx.shape).astype(npd)
+  want = dense.scatter(ul.astype(np.float64), idx, num_nodes)
+  got = gs.scatter(dev(ul), dev(idx), num_nodes).cpu().numpy()
+  assert rel_err(got, want) < (1e-13 if dtype == torch.float64 else 1e-5)
+  with pytest.raises(ValueError, match='rank-1'):
+    gs.gather(dev(np.zeros((3, 3))), dev(idx))
+
+
+def test_scatter_deterministic_segmented():
+  from swirl_fem_b200 import _lib
+  rng = np.random.default_rng(1)
+  num_nodes = 5000
+  idx = rng.integers(0, num_nodes, size=(40000,)).astype(np.int32)
+  idx[:100] = 7            # one very long segment (spans several warps)
+  idx[rng.random(idx.shape) < 0.02] = -1
+  ul = rng.standard_normal(idx.shape)
+  plan = _lib.ScatterPlan(dev(idx), num_nodes)
+  a = plan(dev(ul)).cpu().numpy()
+  b = plan(dev(ul)).cpu().numpy()
+  np.testing.assert_array_equal(a, b)  # bitwise reproducible
+  assert rel_err(a, dense.scatter(ul, idx, num_nodes)) < 1e-13
+  # empty input
+  empty = _lib.ScatterPlan(dev(np.zeros((0,), np.int32)), 5)
+  np.testing.assert_array_equal(
+      empty(dev(np.zeros((0,)))).cpu().numpy(), np.zeros(5))
+
+
+def test_exchange_known_answers():
+  # swirl_fem/core/gather_scatter_test.py:50-130
+  from swirl_fem_b200.core import gather_scatter as gs
+  ni = np.arange(3, dtype=np.int32)
+  gi, ui = gs.get_exchange_indices(ni)
+  u = dev(np.arange(3.))
+  np.testing.assert_array_equal(gs.exchange(u, dev(gi), dev(ui)).cpu(), u.cpu())
+  uni = gs.get_unique_node_indices(ni, periodic_links=np.array([[[0], [2]]]))
+  gi, ui = gs.get_exchange_indices(uni)
+  out = gs.exchange(dev(np.array([1., 2., 3.])), dev(gi), dev(ui))
+  np.testing.assert_allclose(out.cpu().numpy(), [4., 2., 4.])
+  links = np.array([[[0, 1], [6, 7]], [[1, 2], [7, 8]], [[0, 3], [2, 5]],
+                    [[3, 6], [5, 8]]], dtype=np.int32)
+  uni = gs.get_unique_node_indices(np.arange(9, dtype=np.int32), links)
+  gi, ui = gs.get_exchange_indices(uni)
+  out = gs.exchange(dev(np.arange(9.0)), dev(gi), dev(ui))
+  np.testing.assert_allclose(out.cpu().numpy(),
+                             [16., 8., 16., 8., 4., 8., 16., 8., 16.])
+
+
+def test_mesh_api_matches_reference_tests():
+  # swirl_fem/core/mesh_test.py:27-84
+  from swirl_fem_b200.core.interpolation import Nodes1D, NodeType
+  from swirl_fem_b200.core.mesh import Mesh
+  coords = np.array([[0, 0], [0, 1], [1, 0], [1, 1], [2, 0], [2, 1]],
+                    dtype=np.float32)
+  elements = np.array([[0, 1, 2, 3], [2, 3, 4, 5]], dtype=np.int32)
+  mesh = Mesh.create(node_coords=coords, elements=elements)
+  assert (mesh.order, mesh.ndim, mesh.num_nodes, mesh.num_elements,
+          mesh.num_nodes_per_element) == (1, 2, 6, 2, 4)
+  vals = torch.arange(6, dtype=torch.float32).cuda()
+  np.testing.assert_array_equal(mesh.gather(vals).cpu().numpy(),
+                                elements.astype(np.float32))
+  np.testing.assert_array_equal(mesh.element_coords().cpu().numpy(),
+                                coords[elements])
+  with pytest.raises(ValueError, match='shape'):
+    mesh.gather(torch.zeros(5).cuda())
+  c1 = np.linspace(0, 1, 9).reshape(9, 1)
+  e1 = np.array([[i, i + 1] for i in range(8)])
+  with pytest.raises(ValueError, match='number of nodes'):
+    Mesh.create(c1, e1, gridpoints_1d=Nodes1D.create(3, NodeType.NEWTON_COTES))
+
+
+# ----------------------------------------------------------------------------
+# FE space + local covectors vs the reference goldens
+# ----------------------------------------------------------------------------
+
+
+def _golden_cases():
+  g = load_golden('operator')
+  return [str(n) for n in g['names']]
+
+
+def _space_from_golden(g, p, dtype):
+  from swirl_fem_b200.core.fespace import FiniteElementSpace
+  from swirl_fem_b200.core.interpolation import Nodes1D, Quadrature1D
+  from swirl_fem_b200.core.mesh import Mesh
+  ndim, _, n, qt, q = [int(v) for v in g[p + 'meta']]
+  mesh = Mesh.create(g[p + 'node_coords'], g[p + 'elements'],
+                     gridpoints_1d=Nodes1D.create(n, GLL), dtype=dtype)
+  quad = Quadrature1D.create(q, GL if qt == 1 else GLL)
+  return mesh, FiniteElementSpace.create(mesh, quad)
+
+
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+@pytest.mark.parametrize('name', _golden_cases())
+def test_fespace_matches_reference(name, dtype):
+  from swirl_fem_b200.core import fespace as fs
+  from swirl_fem_b200.examples import poisson
+  g = load_golden('operator')
+  p = name + '/'
+  tol = TOL[dtype] * (10 if dtype == torch.float32 else 1)
+  mesh, space = _space_from_golden(g, p, dtype)
+  ndim = mesh.ndim
+  assert rel_err(space.invjacs.cpu(), g[p + 'invjacs']) < tol
+  assert rel_err(space.jacdets.cpu(), g[p + 'jacdets']) < tol
+  assert rel_err(space.quad_coords.cpu(), g[p + 'quad_coords']) < tol
+  u = dev(g[p + 'u'], dtype)
+  u_local = mesh.gather(u)
+  np.testing.assert_array_equal(
+      u_local.cpu().numpy(),
+      g[p + 'u_local'].astype(u_local.cpu().numpy().dtype))
+  uf = space.scalar_function(u_local)
+  vf = space.scalar_function(None)
+  assert rel_err(uf._evaluate().cpu(), g[p + 'eval_u']) < tol
+  assert rel_err(fs.grad(uf)._evaluate().cpu(), g[p + 'eval_grad_u']) < tol
+  assert abs(float(space.integrate(uf)) - float(g[p + 'integral_u'])) < (
+      tol * 10)
+  assert abs(float(space.integrate(lambda x: 1.0)) -
+             float(g[p + 'integral_one'])) < tol * 10
+  got = space.local_covector(poisson.mass_form, (uf, vf))
+  assert rel_err(got.cpu(), g[p + 'mass_local']) < tol
+  got = space.local_covector(poisson.stiffness_form, (uf, vf))
+  assert rel_err(got.cpu(), g[p + 'stiffness_local']) < tol
+  assert rel_err(mesh.scatter(got).cpu(), g[p + 'stiffness']) < tol
+  assert rel_err(mesh.scatter(got, deterministic=True).cpu(),
+                 g[p + 'stiffness']) < tol
+  if p + 'uv' in g.files:
+    uv = dev(g[p + 'uv'], dtype)
+    uv_local = torch.stack([mesh.gather(uv[:, k].contiguous())
+                            for k in range(ndim)], -1)
+    uvf = space.vector_function(uv_local)
+    vvf = space.vector_function(None)
+    assert rel_err(uvf._evaluate().cpu(), g[p + 'eval_uv']) < tol
+    assert rel_err(fs.grad(uvf)._evaluate().cpu(), g[p + 'eval_grad_uv']) < tol
+
+    def vstiff(a, b):  # navier_stokes.py:222-223
+      return lambda x: np.einsum('ij,ij->', fs.grad(a)(x), fs.grad(b)(x))
+
+    def vmass(a, b):  # navier_stokes.py:231-232
+      return lambda x: np.vdot(a(x), b(x))
+
+    assert rel_err(space.local_covector(vstiff, (uvf, vvf)).cpu(),
+                   g[p + 'vstiffness_local']) < tol
+    assert rel_err(space.local_covector(vmass, (uvf, vvf)).cpu(),
+                   g[p + 'vmass_local']) < tol
+    assert abs(float(space.integrate(fs.div(uvf))) -
+               float(g[p + 'integral_div'])) < tol * 10
+
+
+def test_local_covector_rejects_unsupported_forms():
+  from swirl_fem_b200.core import fespace as fs
+  g = load_golden('operator')
+  mesh, space = _space_from_golden(g, 'q2_ne2_p3_gl4/', torch.float64)
+  uf = space.scalar_function(mesh.gather(dev(g['q2_ne2_p3_gl4/u'])))
+  vf = space.scalar_function(None)
+  with pytest.raises(NotImplementedError):
+    space.local_covector(lambda u, v: (lambda x: u(x) * fs.grad(v)(x)[0]),
+                         (uf, vf))
+  with pytest.raises(NotImplementedError):
+    space.local_covector(lambda u, v: (lambda x: x[0] * u(x) * v(x)), (uf, vf))
+  with pytest.raises(ValueError):
+    space.local_covector(lambda u, v: (lambda x: u(x) * v(x)), (uf, uf))
+  with pytest.raises(ValueError, match='shape'):
+    space.scalar_function(torch.zeros(3, 3).cuda())
+
+
+# ----------------------------------------------------------------------------
+# fespace_test.py known answers (swirl_fem/core/fespace_test.py:57-242)
+# ----------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize('ndim', [1, 2, 3])
+@pytest.mark.parametrize('order', [1, 2, 3, 4])
+def test_integrate_single_element(ndim, order):
+  from swirl_fem_b200.core import fespace as fs
+  from swirl_fem_b200.core.interpolation import Quadrature1D
+  from swirl_fem_b200.core.mesh import Mesh
+  num_nodes = (order + 1) ** ndim
+  c1 = np.linspace(0, 1, num=order + 1)
+  coords = np.stack(np.meshgrid(*([c1] * ndim), indexing='ij'),
+                    axis=-1).reshape(num_nodes, ndim)
+  elements = np.arange(num_nodes, dtype=np.int32).reshape((1, num_nodes))
+  mesh = Mesh.create(node_coords=coords, elements=elements)
+  space = fs.FiniteElementSpace.create(mesh, Quadrature1D.create(order + 1, GL))
+  f = lambda x: sum(x[i] ** order for i in range(ndim))
+  assert abs(float(space.integrate(f)) - ndim / (1 + order)) < 1e-12
+  ec = mesh.element_coords()
+  u_local = sum(ec[..., i] ** order for i in range(ndim))
+  nodal = space.scalar_function(u_local)
+  assert abs(float(space.integrate(nodal)) - ndim / (1 + order)) < 1e-12
+  # gradients: analytic (autograd stands in for jax.grad) and nodal
+  assert abs(float(space.integrate(lambda x: fs.grad(f)(x)[0])) - 1) < 1e-12
+  assert abs(float(space.integrate(lambda x: fs.grad(nodal)(x)[0])) - 1) < 1e-11
+
+
+def test_integrate_generic_quad():
+  from swirl_fem_b200.core import fespace as fs
+  from swirl_fem_b200.core.interpolation import Quadrature1D
+  from swirl_fem_b200.core.mesh import Mesh
+  coords = np.array([[0, 0], [0, 1], [1, 0], [1, 2]], dtype=np.float64)
+  mesh = Mesh.create(coords, np.arange(4, dtype=np.int32).reshape((1, 4)))
+  space = fs.FiniteElementSpace.create(mesh, Quadrature1D.create(2, GL))
+  ec = mesh.element_coords()
+  nodal = space.scalar_function(2 * ec[..., 0] - ec[..., 1] + 1)
+  area = 1.5
+  assert abs(float(space.integrate(lambda x: fs.grad(nodal)(x)[0])) -
+             2 * area) < 1e-12
+  assert abs(float(space.integrate(lambda x: fs.grad(nodal)(x)[1])) +
+             area) < 1e-12
+  vec = space.vector_function(
+      torch.stack([2 * ec[..., 0] - ec[..., 1], 3 * ec[..., 1]], -1))
+  assert abs(float(space.integrate(fs.div(vec))) - 5 * area) < 1e-12
+  with pytest.raises(ValueError, match='shape'):
+    space.integrate(vec)
+
+
+# ----------------------------------------------------------------------------
+# fused operator vs oracle
+# ----------------------------------------------------------------------------
+
+
+def _build(ndim, ne, n1d, quad_type, q1d, dtype, seed=None, with_bc=True):
+  from swirl_fem_b200.core.fespace import FiniteElementSpace
+  from swirl_fem_b200.core.interpolation import Quadrature1D
+  refined = helpers.deformed_premesh(ndim, ne, n1d, seed=seed)
+  mesh = refined.finalize(dtype=dtype)
+  space = FiniteElementSpace.create(mesh, Quadrature1D.create(q1d, quad_type))
+  oracle = dense.FESpace(refined.node_coords, refined.elements, n1d,
+                         helpers.TNAME[GLL], q1d, helpers.TNAME[quad_type])
+  bmask = refined.finalize_host()['physical_masks']['boundary']
+  return refined, mesh, space, oracle, (bmask if with_bc else None)
+
+
+CASES_2D = [(2, 3, n, GLL, n) for n in range(2, 17)] + [
+    (2, 3, 5, GL, 5), (2, 2, 9, GL, 10), (2, 3, 4, GL, 6), (2, 2, 3, GLL, 5)]
+CASES_3D = [(3, 2, n, GLL, n) for n in range(2, 10)] + [
+    (3, 1, 12, GLL, 12), (3, 1, 16, GLL, 16),
+    (3, 2, 3, GL, 4), (3, 2, 5, GL, 6), (3, 1, 8, GL, 9)]
+CASES_1D = [(1, 5, 4, GL, 5), (1, 4, 6, GLL, 6)]
+
+
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+@pytest.mark.parametrize('case', CASES_1D + CASES_2D + CASES_3D,
+                         ids=lambda c: f'{c[0]}d_ne{c[1]}_N{c[2]}_{c[3].value[:9]}{c[4]}')
+def test_operator_apply_matches_oracle(case, dtype):
+  ndim, ne, n1d, qt, q1d = case
+  refined, mesh, space, oracle, bmask = _build(ndim, ne, n1d, qt, q1d, dtype,
+                                               seed=ndim * 100 + n1d)
+  rng = np.random.default_rng(n1d)
+  u = rng.standard_normal(mesh.num_nodes)
+  interior = 1.0 - bmask
+  op = space.operator(dirichlet_mask=bmask, with_mass=True)
+  tol = TOL[dtype] * (20 if dtype == torch.float32 else 1)
+  variants = [0, 1] if qt == GLL and q1d == n1d and ndim > 1 else [0]
+  for lam, mu in ((0.0, 1.0), (1.0, 0.0), (1833.3, 0.7)):
+    want = oracle.apply(u, lam=lam, mu=mu, interior_mask=interior)
+    for variant in variants:
+      op.set_variant(variant)
+      dot = torch.zeros((), dtype=torch.float64, device='cuda')
+      got = op.apply(dev(u, dtype), lam=lam, mu=mu, dot_out=dot)
+      assert rel_err(got.cpu(), want) < tol, (lam, mu, variant)
+      assert abs(float(dot) - float(u @ want)) <= tol * 10 * np.abs(
+          u * want).sum()
+    op.set_variant(0)
+  # stiffness-only handle (no mass factors stored) + no boundary mask
+  op2 = space.operator(dirichlet_mask=None, with_mass=False)
+  got = op2.apply(dev(u, dtype))
+  assert rel_err(got.cpu(), oracle.apply(u)) < tol
+  with pytest.raises(ValueError):
+    op2.apply(dev(u, dtype), lam=1.0)
+  # diagonal (K12)
+  d = op.diag(lam=0.0, mu=1.0)
+  assert rel_err(d.cpu(), oracle.stiffness_diag(interior)) < tol
+  # vector field (AoS, component last): component-wise operator
+  uv = rng.standard_normal((mesh.num_nodes, ndim))
+  got = op.apply(dev(uv, dtype), lam=0.3, mu=1.1)
+  want = np.stack([oracle.apply(uv[:, k], lam=0.3, mu=1.1,
+                                interior_mask=interior)
+                   for k in range(ndim)], -1)
+  assert rel_err(got.cpu(), want) < tol
+
+
+def test_operator_properties_large():
+  """Size-independent properties at a size the oracle cannot reach."""
+  from swirl_fem_b200.core.fespace import FiniteElementSpace
+  from swirl_fem_b200.core.interpolation import Quadrature1D
+  refined = helpers.deformed_premesh(3, 10, 8)  # 10^3 p=7: 357,911 dofs
+  mesh = refined.finalize()
+  space = FiniteElementSpace.create(mesh, Quadrature1D.create(8, GLL))
+  op = space.operator(with_mass=False)
+  g = torch.Generator(device='cuda').manual_seed(0)
+  u = torch.randn(mesh.num_nodes, dtype=torch.float64, device='cuda',
+                  generator=g)
+  v = torch.randn(mesh.num_nodes, dtype=torch.float64, device='cuda',
+                  generator=g)
+  au, av = op.apply(u), op.apply(v)
+  scale = float(au.abs().max())
+  # symmetry, constants in the null space, linearity
+  assert abs(float(v @ au) - float(u @ av)) < 1e-11 * float(au.norm() * v.norm())
+  ones = torch.ones_like(u)
+  assert float(op.apply(ones).abs().max()) < 1e-10 * scale
+  lin = op.apply(2.0 * u - 3.0 * v)
+  assert float((lin - (2.0 * au - 3.0 * av)).abs().max()) < 1e-11 * scale
+  # generic kernel agrees with the specialised one at full size
+  op.set_variant(1)
+  assert float((op.apply(u) - au).abs().max()) < 1e-11 * scale
+
+
+# ----------------------------------------------------------------------------
+# CG
+# ----------------------------------------------------------------------------
+
+
+def test_cg_generic_known_answers():
+  # swirl_fem/linalg/cg_test.py:26-50
+  from swirl_fem_b200.linalg.cg import cg
+  b = torch.arange(9.0, dtype=torch.float64).reshape(3, 3).cuda()
+  x, info = cg(lambda v: 2 * v, b)
+  np.testing.assert_allclose(x.cpu().numpy(), (b / 2).cpu().numpy())
+  assert info['num_iterations'] == 1
+  A = lambda v: {'a': v['a'] + 0.5 * v['b'], 'b': 0.5 * v['a'] + v['b']}
+  bb = {'a': torch.tensor(1.0, dtype=torch.float64).cuda(),
+        'b': torch.tensor(-4.0, dtype=torch.float64).cuda()}
+  x, _ = cg(A, bb)
+  assert abs(float(x['a']) - 4.0) < 1e-6 and abs(float(x['b']) + 6.0) < 1e-6
+  A2 = lambda v: torch.stack([2 * v[0], 0 * v[1]])
+  M2 = lambda v: torch.stack([v[0], 0 * v[1]])
+  x, _ = cg(A2, (1 + torch.arange(2.0, dtype=torch.float64)).cuda(), M=M2)
+  np.testing.assert_allclose(x.cpu().numpy(), [0.5, 0.])
+
+
+@pytest.mark.parametrize('tag', ['plain', 'jacobi', 'atol', 'maxiter', 'x0'])
+def test_cg_generic_matches_reference_golden(tag):
+  from swirl_fem_b200.linalg.cg import cg
+  g = load_golden('cg')
+  mat, b = dev(g['mat']), dev(g['b'])
+  dinv = 1.0 / torch.diagonal(mat)
+  kw = {
+      'plain': dict(tol=1e-8),
+      'jacobi': dict(tol=1e-8, M=lambda r: dinv * r),
+      'atol': dict(tol=0., atol=1e-3),
+      'maxiter': dict(tol=1e-14, maxiter=7),
+      'x0': dict(tol=1e-6, x0=torch.ones_like(b)),
+  }[tag]
+  x, info = cg(lambda v: mat @ v, b, **kw)
+  assert abs(info['num_iterations'] - int(g[f'{tag}/num_iterations'])) <= 1
+  assert rel_err(x.cpu(), g[f'{tag}/x']) < 1e-6
+
+
+@pytest.mark.parametrize('precond', [None, 'jacobi'])
+@pytest.mark.parametrize('case', [(2, 8, 5, GL, 5), (2, 6, 5, GLL, 5),
+                                  (3, 3, 4, GL, 5), (3, 3, 5, GLL, 5)])
+def test_fused_cg_matches_oracle(case, precond):
+  from swirl_fem_b200.core.operator import JacobiPreconditioner
+  from swirl_fem_b200.linalg.cg import cg
+  ndim, ne, n1d, qt, q1d = case
+  refined, mesh, space, oracle, bmask = _build(ndim, ne, n1d, qt, q1d,
+                                               torch.float64)
+  interior = 1.0 - bmask
+  op = space.operator(dirichlet_mask=bmask, with_mass=True)
+  f = np.ones(mesh.num_nodes)
+  b_want = oracle.apply(f, lam=1.0, mu=0.0, interior_mask=interior)
+  A_or = lambda v: oracle.apply(v, interior_mask=interior)
+  M_or, M = None, None
+  if precond:
+    diag = oracle.stiffness_diag(interior)
+    minv_or = np.where(diag != 0, 1.0 / np.where(diag != 0, diag, 1.0), 0.0)
+    M_or = lambda r: minv_or * r
+    M = JacobiPreconditioner(op.jacobi_minv())
+  x_want, info_want = dense.cg(A_or, b_want, tol=1e-8, M=M_or)
+  b = op.apply(dev(f), lam=1.0, mu=0.0)
+  assert rel_err(b.cpu(), b_want) < 1e-12
+  x, info = cg(op.bind(0.0, 1.0), b, tol=1e-8, M=M, check_every=5)
+  assert abs(info['num_iterations'] - info_want['num_iterations']) <= 1
+  assert rel_err(x.cpu(), x_want) < 1e-6
+  assert float(info['residual']) <= (1e-8) ** 2 * float(b_want @ b_want) * 1.01
+  # maxiter cut-off and generic path through the same operator
+  x2, info2 = cg(op.bind(0.0, 1.0), b, tol=1e-12, maxiter=3, M=M)
+  assert info2['num_iterations'] == 3
+  xg, infog = cg(lambda v: op.apply(v), b, tol=1e-8,
+                 M=(None if M is None else (lambda r: M(r))))
+  assert abs(infog['num_iterations'] - info_want['num_iterations']) <= 1
+  assert rel_err(xg.cpu(), x_want) < 1e-6
+
+
+def test_config1_poisson_32x32_p4_iteration_counts():
+  """BASELINE config 1: 2-D Poisson 32x32, GLL order 4, (Jacobi-)PCG."""
+  from swirl_fem_b200.examples import poisson
+  refined = helpers.deformed_premesh(2, 32, 5, curved=False)
+  mesh = refined.finalize()
+  assert mesh.num_nodes == 16641
+  f = torch.ones(mesh.num_nodes, dtype=torch.float64, device='cuda')
+  bcs = {'boundary': (poisson.BCType.DIRICHLET, 0.)}
+  u, info = poisson.solve_poisson(mesh, f, bcs, return_info=True)
+  uj, infoj = poisson.solve_poisson(mesh, f, bcs, preconditioner='jacobi',
+                                    return_info=True)
+  oracle = dense.FESpace(refined.node_coords, refined.elements, 5,
+                         helpers.TNAME[GLL], 5, helpers.TNAME[GL])
+  interior = 1.0 - refined.finalize_host()['physical_masks']['boundary']
+  b = oracle.apply(np.ones(mesh.num_nodes), 1.0, 0.0, interior)
+  A = lambda v: oracle.apply(v, interior_mask=interior)
+  x_or, info_or = dense.cg(A, b, tol=1e-5)
+  diag = oracle.stiffness_diag(interior)
+  minv = np.where(diag != 0, 1.0 / np.where(diag != 0, diag, 1.0), 0.0)
+  xj_or, infoj_or = dense.cg(A, b, tol=1e-5, M=lambda r: minv * r)
+  assert abs(info['num_iterations'] - info_or['num_iterations']) <= 1
+  assert abs(infoj['num_iterations'] - infoj_or['num_iterations']) <= 1
+  # BASELINE.md section 5 provisional goldens: 215 (plain) / 208 (Jacobi)
+  assert abs(info_or['num_iterations'] - 215) <= 1
+  assert abs(infoj_or['num_iterations'] - 208) <= 1
+  assert np.abs(u.cpu().numpy() - x_or).max() < 1e-6
+  assert np.abs(uj.cpu().numpy() - xj_or).max() < 1e-6
+
+
+# ----------------------------------------------------------------------------
+# poisson_test.py analytical checks (swirl_fem/examples/poisson_test.py)
+# ----------------------------------------------------------------------------
+
+
+def _line_mesh(num_elements, with_boundary):
+  from swirl_fem_b200.core.premesh import Premesh
+  n = num_elements + 1
+  coords = np.linspace(0, 1, n).reshape((n, 1))
+  elements = np.array([[i, i + 1] for i in range(num_elements)])
+  groups = ({'boundary': np.array([[0, n - 1]], dtype=np.int32)}
+            if with_boundary else None)
+  return Premesh.create(coords, elements, physical_groups=groups).finalize()
+
+
+def test_poisson_1d_unit_and_linear_forcing():
+  from swirl_fem_b200.examples import poisson
+  mesh = _line_mesh(32, True)
+  bcs = {'boundary': (poisson.BCType.DIRICHLET, 0.)}
+  x = mesh.node_coords[:, 0]
+  u = poisson.solve_poisson(mesh, torch.ones_like(x), bcs)
+  np.testing.assert_allclose(u.cpu().numpy(), (.5 * (x - x ** 2)).cpu().numpy(),
+                             rtol=1e-7, atol=1e-12)
+  u = poisson.solve_poisson(mesh, 6 * x, bcs)
+  np.testing.assert_allclose(u.cpu().numpy(), (x - x ** 3).cpu().numpy(),
+                             rtol=1e-7, atol=1e-12)
+
+
+def test_poisson_1d_neumann():
+  from swirl_fem_b200.examples import poisson
+  mesh = _line_mesh(128, False)
+  x = mesh.node_coords[:, 0]
+  forcing = -.5 * np.pi ** 2 * torch.cos(np.pi * x)
+  u = poisson.solve_poisson(mesh, forcing, boundary_conditions={}, rtol=1e-7)
+  expected = torch.sin(.5 * np.pi * x) ** 2 - .5
+  np.testing.assert_allclose(u.cpu().numpy(), expected.cpu().numpy(),
+                             rtol=1e-4, atol=1e-5)
+
+
+def _square_premesh(ne):
+  from swirl_fem_b200.common.premesh_commons import unit_cube_mesh
+  return unit_cube_mesh(ne, ndim=2, a=-1., b=1.)
+
+
+def test_poisson_square_and_unit_circle():
+  from swirl_fem_b200.examples import poisson
+  pm = _square_premesh(32)
+  bcs = {'boundary': (poisson.BCType.DIRICHLET, 0.)}
+  mesh = pm.finalize()
+  u = poisson.solve_poisson(mesh, torch.ones(mesh.num_nodes).cuda().double(),
+                            bcs)
+  x = mesh.node_coords.cpu().numpy()
+  series = np.zeros(len(x))
+  for k in range(1, 10, 2):
+    series += (1 / (k ** 3 * np.sinh(k * np.pi))) * np.sin(
+        k * np.pi * (1 + x[:, 0]) / 2) * (
+            np.sinh(k * np.pi * (1 - x[:, 1]) / 2) +
+            np.sinh(k * np.pi * (1 + x[:, 1]) / 2))
+  expected = (1 - x[:, 0] ** 2) / 2 - (16 / np.pi ** 3) * series
+  np.testing.assert_allclose(u.cpu().numpy(), expected, rtol=1e-6, atol=1e-3)
+  # Coons patch of the unit disk (poisson_test.py:70-90)
+  c = pm.node_coords
+  r2 = 1 / np.sqrt(2)
+  disk = np.stack([
+      c[:, 0] * (np.cos(np.pi * c[:, 1] / 4) - r2) + np.sin(np.pi * c[:, 0] / 4),
+      c[:, 1] * (np.cos(np.pi * c[:, 0] / 4) - r2) + np.sin(np.pi * c[:, 1] / 4),
+  ], -1)
+  mesh = pm.replace(node_coords=disk).finalize()
+  u = poisson.solve_poisson(mesh, torch.ones(mesh.num_nodes).cuda().double(),
+                            bcs)
+  expected = .25 * (1 - (disk ** 2).sum(-1))
+  np.testing.assert_allclose(u.cpu().numpy(), expected, rtol=1e-6, atol=1e-4)
+
+
+def test_no_cpu_fallback():
+  from swirl_fem_b200 import _lib
+  from swirl_fem_b200.core import gather_scatter as gs
+  with pytest.raises(_lib.SwirlB200Error, match='no CPU path'):
+    gs.gather(torch.zeros(4, dtype=torch.float64),
+              torch.zeros(2, dtype=torch.int32))
