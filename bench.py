@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 hot path: matrix-free Laplacian apply (+ fused CG).
+
+Contract: `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line.
+A "step" is one operator apply  y = mask . Z^T K Z x  over the whole mesh
+(N > 1: every rank applies its block, then the shared-dof halo exchange).
+Workload (`config.workload`): BASELINE.json config 4 -- 3-D hex Poisson,
+GLL order 7, ne = 68 elements per axis, 108.5 M global dofs, fp64 -- the
+configuration the metric (GDOF/s apply & CG at 1/2/4/8 B200) is quoted on; it
+fits one B200 (geometric factors 7.7 GB).  Total work is fixed as N grows:
+`scaling: strong`.
+
+  value      whole-job GDOF/s with inputs resident in HBM (CUDA events, max
+             over ranks)
+  e2e        same metric through the public API with pinned HOST buffers:
+             H2D of x, apply, D2H of y inside the timed region
+  roofline   algorithmic bytes of one apply / its measured duration vs the
+             measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the numpy oracle (restated dense reference algorithm, batched
+             GEMM so BLAS threads are used) on a bounded sample, rank 0, N = 1
+  cg         fused PCG: ms / iteration over a fixed number of iterations
+
+`--impl reference` times the reference's algorithm on the host cores (the
+oracle port: JAX is not installable in this image).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+METRIC = 'GDOF/s matrix-free Laplacian apply (3-D hex, GLL order 7, fp64)'
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=5)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--ne', type=int, default=int(os.environ.get('SFEM_NE', 68)))
+  ap.add_argument('--order', type=int, default=7)
+  ap.add_argument('--dim', type=int, default=3)
+  ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'])
+  ap.add_argument('--cg-iters', type=int, default=30)
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-e2e', action='store_true')
+  return ap.parse_args()
+
+
+def deform(x):
+  """Smooth non-affine map so every geometric factor is populated."""
+  ndim = x.shape[-1]
+  perm = np.roll(np.arange(ndim), 1)
+  return x + 0.08 * np.sin(np.pi * x[:, perm]) * (1 - x ** 2)
+
+
+def algorithmic_bytes(num_global, num_local_nodes, ndim, esz, with_mass=False):
+  """B_op of BASELINE.md section 3 for a concrete mesh: read x and write y once
+  (2 s per dof), stream connectivity (4 B) and symmetric factors per local
+  node."""
+  g = ndim * (ndim + 1) // 2 + (1 if with_mass else 0)
+  return 2 * esz * num_global + num_local_nodes * (g * esz + 4)
+
+
+class ClockSampler:
+  """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+  QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,'
+           'clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+           'clocks_event_reasons.hw_thermal_slowdown,'
+           'clocks_event_reasons.sw_thermal_slowdown,'
+           'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, gpu_index: int):
+    self.gpu_index = gpu_index
+    self.proc = None
+    self.lines = []
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', f'--id={self.gpu_index}',
+           f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+           '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+          text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+    time.sleep(0.15)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+    sm, smax, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+             'sw_power_cap']
+    for line in self.lines:
+      parts = [p.strip() for p in line.split(',')]
+      if len(parts) < 9:
+        continue
+      try:
+        sm.append(float(parts[1]))
+        smax.append(float(parts[2]))
+      except ValueError:
+        continue
+      for name, val in zip(names, parts[5:9]):
+        if val.lower().startswith('active'):
+          reasons.add(name)
+    return {'sm_mhz': float(np.median(sm)) if sm else None,
+            'sm_max_mhz': float(max(smax)) if smax else None,
+            'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def measured_peak_gbs():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  try:
+    with open(path) as f:
+      return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+  except (OSError, KeyError, ValueError):
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ----------------------------------------------------------------------------
+# CPU legs (oracle port of the reference's dense algorithm)
+# ----------------------------------------------------------------------------
+
+
+def cpu_oracle_throughput(ndim, order, budget_s=12.0, ne_sample=None):
+  """GDOF/s of the numpy oracle (dense Kronecker algorithm of the reference,
+  batched GEMM) on a bounded sample of the same workload."""
+  from oracle import dense
+  from swirl_fem_b200.common.premesh_commons import unit_cube_mesh
+  from swirl_fem_b200.core.interpolation import Nodes1D, NodeType
+  from swirl_fem_b200.core.mesh_refiner import refine_premesh
+  n1d = order + 1
+  if ne_sample is None:
+    ne_sample = 6 if ndim == 3 else 48
+  gll = NodeType.GAUSS_LOBATTO_LEGENDRE
+  refined = refine_premesh(unit_cube_mesh(ne_sample, ndim=ndim, a=-1., b=1.),
+                           Nodes1D.create(n1d, gll))
+  coords = deform(refined.node_coords)
+  fes = dense.FESpace(coords, refined.elements, n1d, 'gauss_lobatto_legendre',
+                      n1d, 'gauss_lobatto_legendre')
+  u = np.random.default_rng(0).standard_normal(refined.num_nodes)
+  fes.apply_gemm(u)  # warm-up (BLAS threads, caches)
+  t0 = time.perf_counter()
+  reps = 0
+  while True:
+    fes.apply_gemm(u)
+    reps += 1
+    el = time.perf_counter() - t0
+    if el > budget_s or reps >= 200:
+      break
+  cores = len(os.sched_getaffinity(0))
+  return {
+      'value': refined.num_nodes * reps / el / 1e9,
+      'unit': 'GDOF/s',
+      'cores': cores,
+      'kind': 'port',
+      'sample': (f'{ndim}-D ne={ne_sample} order {order} '
+                 f'({refined.num_nodes} dofs), {reps} applies in {el:.1f} s, '
+                 'numpy restatement of the reference dense-Kronecker apply '
+                 '(JAX unavailable in image)'),
+      'ms_per_step': el / reps * 1e3,
+  }
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', 0))
+  if rank != 0:
+    return
+  res = cpu_oracle_throughput(args.dim, args.order,
+                              budget_s=max(2.0, 4.0 * args.steps / 10))
+  line = {
+      'impl': 'reference',
+      'metric': METRIC, 'value': res['value'], 'unit': 'GDOF/s',
+      'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': res['ms_per_step'], 'higher_is_better': True,
+      'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+      'data': 'synthetic',
+      'config': {'workload': config_name(args), 'note': (
+          'reference algorithm on host cores over a bounded sample of the '
+          'workload (the dense path is ~55x the flops of sum-factorisation)')},
+      'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind',
+                                           'sample')},
+      'e2e': {'value': res['value'], 'unit': 'GDOF/s',
+              'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+      'gpu_launches': 0,
+  }
+  print(json.dumps(line), flush=True)
+
+
+def config_name(args):
+  p = args.order
+  return (f'{args.dim}-D hex Poisson, GLL order {p}, ne={args.ne} per axis, '
+          f'{(args.ne * p + 1) ** args.dim} global dofs, deformed (non-affine) '
+          'elements, homogeneous Dirichlet, collocated GLL quadrature')
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+
+
+def run_ours(args):
+  import torch
+  import torch.distributed as dist
+  from swirl_fem_b200 import _lib
+  from swirl_fem_b200.communication import partition as part
+  from swirl_fem_b200.core.interpolation import Nodes1D, NodeType, Quadrature1D
+  from swirl_fem_b200.core.mesh import Mesh
+  from swirl_fem_b200.core.operator import FusedOperator
+  from swirl_fem_b200.core.operator import JacobiPreconditioner
+  from swirl_fem_b200.linalg.cg import cg
+
+  world = int(os.environ.get('WORLD_SIZE', 1))
+  rank = int(os.environ.get('RANK', 0))
+  local_rank = int(os.environ.get('LOCAL_RANK', 0))
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
+  torch.cuda.set_device(local_rank)
+  device = torch.device('cuda', local_rank)
+  if world > 1:
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    dist.init_process_group('nccl', device_id=device)
+  assert world == args.gpus or world == 1, (world, args.gpus)
+
+  dtype = torch.float64 if args.dtype == 'f64' else torch.float32
+  esz = 8 if args.dtype == 'f64' else 4
+  gll = NodeType.GAUSS_LOBATTO_LEGENDRE
+  grid1d = Nodes1D.create(args.order + 1, gll)
+
+  t_setup = time.perf_counter()
+  blk = part.block_partition(args.ne, args.dim, grid1d, rank, world)
+  coords = deform(blk.premesh.node_coords)
+  mesh = Mesh.create(coords, blk.premesh.elements, gridpoints_1d=grid1d,
+                     device=device, dtype=dtype)
+  quad = Quadrature1D.create_from_nodes_1d(grid1d)
+  # Only the fused operator is needed: no invjacs / jacdets / quad_coords.
+  op = FusedOperator(mesh, quad, dirichlet_mask=blk.dirichlet, with_mass=False)
+  halo = None
+  if world > 1:
+    gathered = [None] * world
+    dist.all_gather_object(gathered, np.sort(blk.interface_global))
+    halo = part.halo_plan_from_interfaces(
+        rank, blk.interface_local, blk.interface_global, gathered,
+        mesh.num_nodes)
+  torch.cuda.synchronize()
+  t_setup = time.perf_counter() - t_setup
+
+  num_global = blk.num_global_dofs
+  num_local_nodes = mesh.num_elements * mesh.num_nodes_per_element
+  gen = torch.Generator(device=device).manual_seed(1234 + rank)
+  x = torch.randn(mesh.num_nodes, dtype=dtype, device=device, generator=gen)
+  y = torch.empty_like(x)
+
+  def step():
+    op.apply(x, lam=0.0, mu=1.0, out=y)
+    if halo is not None:
+      halo.exchange_(y)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for _ in range(max(args.warmup, 3)):
+    step()
+  barrier()
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  launches0 = _lib.launch_count()
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+  barrier()
+  ev[0].record()
+  for i in range(args.steps):
+    step()
+    ev[i + 1].record()
+  barrier()
+  launches = _lib.launch_count() - launches0
+  clocks = sampler.stop() if rank == 0 else None
+  total_ms = ev[0].elapsed_time(ev[-1])
+  if world > 1:
+    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+  ms_per_step = total_ms / args.steps
+  value = num_global / (ms_per_step * 1e-3) / 1e9
+
+  # roofline of the dominant kernel: per-rank algorithmic bytes / apply time
+  apply_ms = []
+  for i in range(min(args.steps, 10)):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(
+        enable_timing=True)
+    a.record()
+    op.apply(x, lam=0.0, mu=1.0, out=y)
+    b.record()
+    torch.cuda.synchronize()
+    apply_ms.append(a.elapsed_time(b))
+  apply_ms = float(np.mean(apply_ms))
+  abytes = algorithmic_bytes(mesh.num_nodes, num_local_nodes, args.dim, esz)
+  peak, peak_src = measured_peak_gbs()
+  achieved = abytes / (apply_ms * 1e-3) / 1e9
+  roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+              'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+              'peak_source': peak_src,
+              'kernel': 'apply3d_kernel (memset of shared-dof prefix + fused '
+                        'gather/operator/scatter)',
+              'algorithmic_bytes_per_launch': abytes,
+              'kernel_ms': apply_ms,
+              'frac_of_nominal_8TBs': achieved / 8000.0}
+
+  # end to end through the public API with pinned host buffers
+  e2e = None
+  if not args.no_e2e:
+    xh = torch.empty(mesh.num_nodes, dtype=dtype).pin_memory()
+    yh = torch.empty(mesh.num_nodes, dtype=dtype).pin_memory()
+    xh.copy_(x)
+    xd = torch.empty_like(x)
+    n_e2e = max(2, min(args.steps, 5))
+
+    def e2e_step():
+      xd.copy_(xh, non_blocking=True)
+      op.apply(xd, lam=0.0, mu=1.0, out=y)
+      if halo is not None:
+        halo.exchange_(y)
+      yh.copy_(y, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(
+        enable_timing=True)
+    a.record()
+    for _ in range(n_e2e):
+      e2e_step()
+    b.record()
+    barrier()
+    e2e_ms = a.elapsed_time(b) / n_e2e
+    if world > 1:
+      t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      e2e_ms = float(t.item())
+    e2e = {'value': num_global / (e2e_ms * 1e-3) / 1e9, 'unit': 'GDOF/s',
+           'h2d_bytes_per_step': int(mesh.num_nodes * esz),
+           'd2h_bytes_per_step': int(mesh.num_nodes * esz),
+           'ms_per_step': e2e_ms, 'steps': n_e2e}
+
+  # fused CG: fixed iteration count (tol = 0 never converges early)
+  cg_info = None
+  if args.cg_iters > 0 and world == 1:
+    ones = torch.ones(mesh.num_nodes, dtype=dtype, device=device)
+    rhs = op.apply(ones, lam=0.0, mu=1.0) * 0 + torch.where(
+        torch.as_tensor(blk.dirichlet, device=device), 0.0, 1.0).to(dtype)
+    minv = JacobiPreconditioner(op.jacobi_minv())
+    cg(op.bind(0.0, 1.0), rhs, tol=0.0, maxiter=3, M=minv)  # warm-up
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(
+        enable_timing=True)
+    a.record()
+    _, info = cg(op.bind(0.0, 1.0), rhs, tol=0.0, maxiter=args.cg_iters,
+                 M=minv, check_every=args.cg_iters)
+    b.record()
+    torch.cuda.synchronize()
+    cg_ms = a.elapsed_time(b) / max(info['num_iterations'], 1)
+    cg_bytes = abytes + 11 * esz * mesh.num_nodes
+    cg_info = {'iterations': info['num_iterations'], 'ms_per_iteration': cg_ms,
+               'gdof_per_s_iter': num_global / (cg_ms * 1e-3) / 1e9,
+               'preconditioner': 'jacobi',
+               'roofline_frac': cg_bytes / (cg_ms * 1e-3) / 1e9 / peak}
+
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    cpu = cpu_oracle_throughput(args.dim, args.order)
+    cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+
+  if rank == 0:
+    line = {
+        'metric': METRIC if (args.dim, args.order, args.dtype) == (
+            3, 7, 'f64') else (f'GDOF/s matrix-free Laplacian apply '
+                               f'({args.dim}-D, order {args.order}, '
+                               f'{args.dtype})'),
+        'value': value, 'unit': 'GDOF/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': args.dtype,
+        'data': 'synthetic',
+        'config': {
+            'workload': config_name(args),
+            'partition': 'x'.join(str(g) for g in blk.grid),
+            'local_dofs_rank0': mesh.num_nodes,
+            'elements_rank0': mesh.num_elements,
+            'l2_policy': 'inputs larger than L2 (geometric factors '
+                         f'{op.geom.numel() * esz / 1e9:.2f} GB per rank)',
+            'setup_s': t_setup,
+        },
+        'clocks': clocks,
+        'e2e': e2e,
+        'gpu_launches': int(launches),
+        'roofline': roofline,
+        'cpu_baseline': cpu,
+        'cg': cg_info,
+    }
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main():
+  args = parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_ours(args)
+
+
+if __name__ == '__main__':
+  main()

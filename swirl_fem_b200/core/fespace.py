@@ -408,8 +408,8 @@ class FiniteElementSpace:
            bool(with_mass))
     op = self._cache.get(key)
     if op is None:
-      op = FusedOperator(self, dirichlet_mask=dirichlet_mask,
-                         with_mass=with_mass)
+      op = FusedOperator(self.mesh, self.quadrature,
+                         dirichlet_mask=dirichlet_mask, with_mass=with_mass)
       self._cache[key] = op
     return op
 

@@ -24,20 +24,30 @@ from swirl_fem_b200 import _lib
 
 
 class FusedOperator:
-  """`sfem_op` handle bound to a `FiniteElementSpace`."""
+  """`sfem_op` handle: fused operator on a mesh + quadrature rule."""
 
-  def __init__(self, fespace, dirichlet_mask=None, with_mass: bool = True):
-    self.fespace = fespace
-    mesh = fespace.mesh
-    interp = fespace.interpolator
+  def __init__(self, mesh, quadrature, dirichlet_mask=None,
+               with_mass: bool = True):
+    """Builds the operator on `mesh` with the 1-D `quadrature` rule.
+
+    Only the packed symmetric factors are computed (K11); no `invjacs` /
+    `jacdets` arrays are materialised, so this is also the cheap way to set up
+    the >=100 M-dof configuration.
+    """
+    from swirl_fem_b200.core.interpolation import BarycentricInterpolator  # pylint: disable=g-import-not-at-top
+    self.mesh = mesh
+    self.quadrature = quadrature
+    interp = BarycentricInterpolator(
+        ndim=mesh.ndim, gridpoints_1d=mesh.gridpoints_1d,
+        evalpoints_1d=quadrature.nodes)
     b, bd = interp.matrices_1d()
-    self.dtype = fespace.dtype
+    self.dtype = mesh.node_coords.dtype
     self.desc = _lib.Desc(
         dim=mesh.ndim, n1d=mesh.gridpoints_1d.num_points,
-        q1d=fespace.quadrature.num_points, dtype=self.dtype,
+        q1d=quadrature.num_points, dtype=self.dtype,
         collocated=interp.collocated, elements=mesh.elements,
         node_coords=mesh.node_coords, interp_1d=b, interp_grad_1d=bd,
-        quad_weights_1d=fespace.quadrature.weights)
+        quad_weights_1d=quadrature.weights)
     dev = mesh.device
     self.with_mass = bool(with_mass)
     if dirichlet_mask is not None:
@@ -116,7 +126,7 @@ class FusedOperator:
 
   def diag(self, lam: float = 0.0, mu: float = 1.0) -> torch.Tensor:
     """diag(mask . Z^T (lam M + mu K) Z): the Jacobi preconditioner's input."""
-    dev = self.fespace.mesh.device
+    dev = self.mesh.device
     d = torch.empty(self.num_nodes, dtype=self.dtype, device=dev)
     with torch.cuda.device(dev):
       _lib._check(_lib.lib().sfem_op_diag(

@@ -187,64 +187,68 @@ __device__ __forceinline__ void invert(int dim, const T* J, T* inv, T* det) {
 }
 
 // ---------------------------------------------------------------------------
-// K11: geometric factors
+// K11: geometric factors.  Always computed in fp64 (differentiating the
+// coordinates amplifies rounding by ~||D||), stored in the path dtype T.
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kGenericThreads)
-geom_kernel(GenShape s, const T* __restrict__ gtab,
+geom_kernel(GenShape s, const double* __restrict__ gtab,
             const int32_t* __restrict__ elements,
             const T* __restrict__ node_coords, int64_t E,
             T* __restrict__ invjacs, T* __restrict__ jacdets,
             T* __restrict__ quad_coords, T* __restrict__ gf, int ngeom,
-            int with_mass) {
+            int with_mass, double* __restrict__ jq_scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* smem = reinterpret_cast<T*>(smem_raw);
-  GenTables<T> tb;
+  double* smem = reinterpret_cast<double*>(smem_raw);
+  GenTables<double> tb;
   load_tables(s, gtab, smem, &tb);
   const int d = s.dim;
-  const int big = max(s.n, s.q) * max(s.N, s.Q) / min(s.N, s.Q) + 1;
-  (void)big;
   const int tmax = ipow(max(s.N, s.Q), d);
-  T* X = smem + table_elems(s.N, s.Q);  // coords, component-major (d, n)
-  T* Jq = X + d * s.n;                  // (d*d, q): J[i][j] at [i*d+j]
-  T* Xq = Jq + d * d * s.q;             // (d, q) quad coords
-  T* t0 = Xq + d * s.q;
-  T* t1 = t0 + tmax;
+  double* X = smem + table_elems(s.N, s.Q);  // one coordinate component (n)
+  double* Xq = X + s.n;                      // its values at quad points (q)
+  double* t0 = Xq + s.q;
+  double* t1 = t0 + tmax;
+  // J[i][j] at [(i*d+j)*q + p]: shared memory when it fits, else a per-CTA
+  // slice of a global scratch buffer (large N in 3-D)
+  double* Jq = jq_scratch ? jq_scratch + (int64_t)blockIdx.x * d * d * s.q
+                          : t1 + tmax;
 
   for (int64_t e = blockIdx.x; e < E; e += gridDim.x) {
-    for (int i = threadIdx.x; i < s.n; i += blockDim.x) {
-      const int32_t g = elements[e * s.n + i];
-      for (int j = 0; j < d; ++j)
-        X[j * s.n + i] = g == SFEM_SENTINEL ? T(0) : node_coords[(int64_t)g * d + j];
-    }
-    __syncthreads();
     for (int j = 0; j < d; ++j) {
-      if (quad_coords) forward<T>(s, tb, -1, X + j * s.n, Xq + j * s.q, t0, t1);
+      for (int i = threadIdx.x; i < s.n; i += blockDim.x) {
+        const int32_t g = elements[e * s.n + i];
+        X[i] =
+            g == SFEM_SENTINEL ? 0.0 : (double)node_coords[(int64_t)g * d + j];
+      }
+      __syncthreads();
+      if (quad_coords) {
+        forward<double>(s, tb, -1, X, Xq, t0, t1);
+        for (int p = threadIdx.x; p < s.q; p += blockDim.x)
+          quad_coords[(e * s.q + p) * d + j] = (T)Xq[p];
+      }
       for (int i = 0; i < d; ++i)
-        forward<T>(s, tb, i, X + j * s.n, Jq + (i * d + j) * s.q, t0, t1);
+        forward<double>(s, tb, i, X, Jq + (i * d + j) * s.q, t0, t1);
     }
     for (int p = threadIdx.x; p < s.q; p += blockDim.x) {
-      T J[9], inv[9], det;
+      double J[9], inv[9], det;
       for (int a = 0; a < d * d; ++a) J[a] = Jq[a * s.q + p];
-      invert<T>(d, J, inv, &det);
+      invert<double>(d, J, inv, &det);
       const int64_t eq = e * s.q + p;
       if (invjacs)
-        for (int a = 0; a < d * d; ++a) invjacs[eq * d * d + a] = inv[a];
-      if (jacdets) jacdets[eq] = det;
-      if (quad_coords)
-        for (int j = 0; j < d; ++j) quad_coords[eq * d + j] = Xq[j * s.q + p];
+        for (int a = 0; a < d * d; ++a) invjacs[eq * d * d + a] = (T)inv[a];
+      if (jacdets) jacdets[eq] = (T)det;
       if (gf) {
-        const T wd = quad_weight<T>(s, tb.W, p) * det;
+        const double wd = quad_weight<double>(s, tb.W, p) * det;
         T* g = gf + e * (int64_t)ngeom * s.q + p;
         int c = 0;
         for (int i = 0; i < d; ++i)
           for (int k = i; k < d; ++k) {
-            T acc = T(0);
+            double acc = 0.0;
             for (int j = 0; j < d; ++j) acc += inv[j * d + i] * inv[j * d + k];
-            g[(int64_t)c * s.q] = wd * acc;
+            g[(int64_t)c * s.q] = (T)(wd * acc);
             ++c;
           }
-        if (with_mass) g[(int64_t)c * s.q] = wd;
+        if (with_mass) g[(int64_t)c * s.q] = (T)wd;
       }
     }
     __syncthreads();
@@ -534,17 +538,28 @@ int launch_geom(const SpaceBase& b, void* invjacs, void* jacdets,
   const GenShape s = make_shape(b);
   const int d = s.dim;
   const int tmax = ipow_host(s.N > s.Q ? s.N : s.Q, d);
-  const size_t elems = table_elems(s.N, s.Q) + (size_t)d * s.n +
-                       (size_t)d * d * s.q + (size_t)d * s.q + 2 * (size_t)tmax;
-  const size_t bytes = elems * sizeof(T);
-  int rc = prepare_smem(geom_kernel<T>, bytes);
-  if (rc) return rc;
+  const size_t base = table_elems(s.N, s.Q) + (size_t)s.n + (size_t)s.q +
+                      2 * (size_t)tmax;
+  const size_t jq = (size_t)d * d * s.q;
   const int64_t E = b.desc.num_elements;
   if (E == 0) return SFEM_OK;
-  geom_kernel<T><<<grid_for(E, 4), kGenericThreads, bytes, stream>>>(
-      s, tables<T>(b), b.desc.elements, (const T*)b.desc.node_coords, E,
-      (T*)invjacs, (T*)jacdets, (T*)quad_coords, (T*)gf, ngeom, with_mass);
+  const bool spill_jq = (base + jq) * sizeof(double) > 160 * 1024;
+  const size_t bytes = (base + (spill_jq ? 0 : jq)) * sizeof(double);
+  int rc = prepare_smem(geom_kernel<T>, bytes);
+  if (rc) return rc;
+  const int grid = grid_for(E, spill_jq ? 1 : 4);
+  double* scratch = nullptr;
+  if (spill_jq)
+    SFEM_CUDA_CHECK(cudaMalloc(&scratch, sizeof(double) * jq * (size_t)grid));
+  geom_kernel<T><<<grid, kGenericThreads, bytes, stream>>>(
+      s, b.d_tables64, b.desc.elements, (const T*)b.desc.node_coords, E,
+      (T*)invjacs, (T*)jacdets, (T*)quad_coords, (T*)gf, ngeom, with_mass,
+      scratch);
   SFEM_LAUNCH_CHECK();
+  if (scratch) {
+    SFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    cudaFree(scratch);
+  }
   return SFEM_OK;
 }
 
