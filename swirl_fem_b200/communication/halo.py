@@ -93,22 +93,29 @@ class HaloPlan:
       self._dev[key] = (idx, send, recv)
     return self._dev[key]
 
+  # The two device steps; the CPU (gloo) tests of the exchange *protocol*
+  # override them, the product path is CUDA only.
+  def _pack(self, u, idx, buf):
+    _lib.halo_pack(u, idx, buf)
+
+  def _unpack_add(self, u, idx, buf):
+    _lib.halo_unpack_add(u, idx, buf)
+
   def exchange_(self, u: torch.Tensor) -> torch.Tensor:
-    """In-place QQ^T on this rank's `(num_local_nodes,)` CUDA vector."""
+    """In-place QQ^T on this rank's `(num_local_nodes,)` vector."""
     import torch.distributed as dist  # pylint: disable=g-import-not-at-top
-    _lib.require_cuda(u)
     if not self.peers:
       return u
     idx, send, recv = self._device_lists(u.device, u.dtype)
     ops = []
     for q in self.peers:
-      _lib.halo_pack(u, idx[q], send[q])
+      self._pack(u, idx[q], send[q])
       ops.append(dist.P2POp(dist.isend, send[q], q, group=self.group))
       ops.append(dist.P2POp(dist.irecv, recv[q], q, group=self.group))
     for work in dist.batch_isend_irecv(ops):
       work.wait()
     for q in self.peers:
-      _lib.halo_unpack_add(u, idx[q], recv[q])
+      self._unpack_add(u, idx[q], recv[q])
     return u
 
   def exchange(self, u: torch.Tensor) -> torch.Tensor:

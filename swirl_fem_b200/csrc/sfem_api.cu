@@ -104,7 +104,7 @@ static int apply_dispatch(const sfem_op& op, double lambda, double mu,
                           const void* x, void* y, int ncomp, bool local,
                           double* dot_xy, cudaStream_t stream) {
   const sfem_space_desc& d = op.base.desc;
-  if (op.variant == 0 && d.collocated && d.n1d <= 16 &&
+  if (op.variant != 1 && d.collocated && d.n1d <= 16 &&
       (d.dim == 2 || d.dim == 3)) {
     return d.dim == 2 ? launch_apply_colloc_dim<T, 2>(op, lambda, mu, x, y,
                                                       ncomp, local, dot_xy,
@@ -271,7 +271,7 @@ void sfem_op_destroy(sfem_op* op) {
 
 int sfem_op_set_variant(sfem_op* op, int32_t variant) {
   using namespace sfem;
-  SFEM_REQUIRE(op && (variant == 0 || variant == 1), "bad variant");
+  SFEM_REQUIRE(op && variant >= 0 && variant <= 31, "bad variant");
   op->variant = variant;
   return SFEM_OK;
 }

@@ -1,0 +1,145 @@
+"""N > 1 host logic on CPU: halo plans and the exchange protocol over gloo.
+
+The pack / unpack-add steps are CUDA kernels in the product; here they are
+replaced by index ops (test double) so that the *plan* and the *message
+protocol* (who sends what to whom, in which order) are exercised with
+world_size 2 and 4 on the CPU.  The wire results are compared with the
+unpartitioned QQ^T semantics of the reference
+(swirl_fem/core/gather_scatter.py:221-261) and its known answers
+(swirl_fem/core/gather_scatter_test.py:157-263).
+"""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from swirl_fem_b200.communication import partition as part
+from swirl_fem_b200.communication.halo import HaloPlan
+from swirl_fem_b200.core import gather_scatter as gs
+from swirl_fem_b200.core.interpolation import Nodes1D
+from swirl_fem_b200.core.interpolation import NodeType
+
+GLL = NodeType.GAUSS_LOBATTO_LEGENDRE
+
+
+class CpuHaloPlan(HaloPlan):
+  """HaloPlan with the two device kernels replaced by CPU index ops."""
+
+  def _pack(self, u, idx, buf):
+    buf.copy_(u[idx.long()])
+
+  def _unpack_add(self, u, idx, buf):
+    u[idx.long()] += buf
+
+
+def _free_port():
+  with socket.socket() as s:
+    s.bind(('127.0.0.1', 0))
+    return s.getsockname()[1]
+
+
+def _worker_known_answers(rank, world, port, node_indices, u_all, expected):
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    base = HaloPlan.from_node_indices(node_indices, rank)
+    plan = CpuHaloPlan(**{f: getattr(base, f) for f in
+                          ('rank', 'world', 'peers', 'local_idx', 'owned')})
+    u = torch.tensor(u_all[rank], dtype=torch.float64)
+    out = plan.exchange(u)
+    np.testing.assert_array_equal(out.numpy(), expected[rank])
+  finally:
+    dist.destroy_process_group()
+
+
+def _run(fn, world, *args):
+  mp.spawn(fn, args=(world, _free_port()) + args, nprocs=world, join=True)
+
+
+def test_exchange_known_answers_4_ranks():
+  # gather_scatter_test.py:157-177
+  ni = np.array([[0, 1, 2], [2, 3, 4], [4, 5, 6], [6, 7, 8]], dtype=np.int32)
+  u = np.arange(12.).reshape(4, 3)
+  expected = np.array([[0, 1, 5], [5, 4, 11], [11, 7, 17], [17, 10, 11]],
+                      dtype=np.float64)
+  _run(_worker_known_answers, 4, ni, u, expected)
+  # periodic 0 <-> 8 (gather_scatter_test.py:200-223)
+  nip = gs.get_unique_node_indices(ni, periodic_links=np.array([[[0], [8]]]))
+  expected = np.array([[11, 1, 5], [5, 4, 11], [11, 7, 17], [17, 10, 11]],
+                      dtype=np.float64)
+  _run(_worker_known_answers, 4, nip, u, expected)
+
+
+def test_exchange_doubly_periodic_4_ranks():
+  # gather_scatter_test.py:225-263: every global node receives four ones
+  ni = np.array([[0, 1, 3, 4], [1, 2, 4, 5], [3, 4, 6, 7], [4, 5, 7, 8]],
+                dtype=np.int32)
+  links = np.array([[[0, 1], [6, 7]], [[1, 2], [7, 8]], [[0, 3], [2, 5]],
+                    [[3, 6], [5, 8]]], dtype=np.int32)
+  nip = gs.get_unique_node_indices(ni, periodic_links=links)
+  _run(_worker_known_answers, 4, nip, np.ones((4, 4)), 4 * np.ones((4, 4)))
+
+
+def _worker_block(rank, world, port, ndim, ne, n1d):
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    blk = part.block_partition(ne, ndim, Nodes1D.create(n1d, GLL), rank, world)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, np.sort(blk.interface_global))
+    base = part.halo_plan_from_interfaces(
+        rank, blk.interface_local, blk.interface_global, gathered,
+        blk.premesh.num_nodes)
+    plan = CpuHaloPlan(**{f: getattr(base, f) for f in
+                          ('rank', 'world', 'peers', 'local_idx', 'owned')})
+    # a global field sampled at the local nodes: f(x) = 1 + x0 + 2 x1 (+3 x2)
+    x = blk.premesh.node_coords
+    f = 1.0 + sum((k + 1) * x[:, k] for k in range(ndim))
+    u = torch.tensor(f, dtype=torch.float64)
+    out = plan.exchange(u).numpy()
+    # multiplicity of every local node over ranks
+    mult = plan.exchange(torch.ones_like(u)).numpy()
+    np.testing.assert_allclose(out, mult * f, rtol=1e-13)
+    # owned weights count every global dof exactly once
+    total = torch.tensor([float(plan.owned.sum())], dtype=torch.float64)
+    dist.all_reduce(total)
+    assert int(total.item()) == blk.num_global_dofs
+    # interface nodes have multiplicity >= 2, interior ones 1
+    interior = np.ones(len(f), dtype=bool)
+    interior[blk.interface_local] = False
+    assert (mult[interior] == 1).all()
+    assert (mult[blk.interface_local] >= 2).all()
+    assert mult.max() <= 2 ** ndim
+    # Dirichlet flags = global boundary only
+    onb = (np.abs(np.abs(x) - 1.0) < 1e-12).any(axis=1)
+    np.testing.assert_array_equal(blk.dirichlet, onb)
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,ndim,ne,n1d', [(2, 2, 4, 4), (2, 3, 2, 3),
+                                               (4, 3, 2, 4), (4, 2, 4, 3)])
+def test_block_partition_halo(world, ndim, ne, n1d):
+  _run(_worker_block, world, ndim, ne, n1d)
+
+
+def test_plan_from_reference_partition_golden():
+  """HaloPlan lists agree with the reference's exchange_gather_indices."""
+  from tests.conftest import load_golden
+  g = load_golden('partition')
+  for name in ('q2_ne4_p2_2x2', 'h3_ne2_p2_2x2x2', 'q2_ne4_p3_2x1'):
+    ni = g[name + '/node_indices']
+    gi = g[name + '/exchange_gather_indices']
+    world = len(ni)
+    for r in range(world):
+      plan = HaloPlan.from_node_indices(ni, r)
+      shared_local = np.unique(np.concatenate(
+          [plan.local_idx[q] for q in plan.peers])) if plan.peers else []
+      np.testing.assert_array_equal(np.sort(gi[r][gi[r] >= 0]), shared_local)
