@@ -2,18 +2,23 @@
 //
 // N^2 threads per element.  The same thread index (p, q) = (t / N, t % N) is
 // interpreted under three mappings, one per tensor axis, so that every 1-D
-// contraction runs entirely in registers against D[i][j] with COMPILE-TIME
-// (i, j) -- uniform-register / constant-bank operands, no per-thread registers
-// or shared-memory traffic for the derivative matrix:
+// contraction runs entirely in registers against compile-time-indexed matrix
+// entries (uniform-register / constant-bank operands; no per-thread registers
+// or shared-memory traffic for the derivative matrix):
 //   mapping A: thread owns the a0-column  u[:, p, q]
 //   mapping B: thread owns the a1-column  u[p, :, q]
 //   mapping C: thread owns the a2-column  u[p, q, :]
-// Columns are exchanged through padded shared-memory tiles (u double-buffered,
-// two work tiles); per element there are 4 block barriers (the slab-sweep
-// kernel v1 needs 2N) and every contraction exposes N independent FMA chains.
-// Nothing but the connectivity words and the a0-part of the result lives in
-// registers across barriers, which keeps the fp64 kernel at <= 128 registers
-// (2 CTAs of 256 threads per SM).
+// Columns are exchanged through XOR-swizzled shared-memory tiles (u
+// double-buffered + two work tiles) that are bank-conflict free under all
+// three mappings; per element there are 4 block barriers (the slab-sweep
+// kernel v1 needs 2N).
+//
+// Contractions use the even-odd decomposition of the GLL differentiation
+// matrix (D is centro-antisymmetric because the nodes are symmetric):
+//   E_j = sum_m Ae[j][m] (c[m] + c[N-1-m]),  O_j = sum_m Ao[j][m] (c[m] - c[N-1-m])
+//   out[j] = E_j + O_j,  out[N-1-j] = O_j - E_j
+// which halves the multiply count and the number of matrix-entry fetches (on
+// sm_100a every fp64 entry costs one LDCU: DFMA takes no constant operand).
 //
 // Memory pipeline (persistent CTAs, one wave):
 //   * the gather x[idx] of the CTA's NEXT element is issued with cp.async
@@ -31,10 +36,84 @@
 namespace sfem {
 namespace {
 
+// Even-odd factors of D (apply) and D^T (transposed apply).
 template <typename T, int N>
-struct DMat3 {
-  T d[N * N];  // row-major D[i][j] = l_j'(x_i)
+struct EvenOdd {
+  static constexpr int H = N / 2;
+  static constexpr int HS = H > 0 ? H : 1;
+  T ae[HS * HS];   // (D[j][m] + D[j][N-1-m]) / 2
+  T ao[HS * HS];   // (D[j][m] - D[j][N-1-m]) / 2
+  T mid_col[HS];   // odd N: D[j][H]
+  T mid_row[HS];   // odd N: D[H][m]
 };
+
+template <typename T, int N>
+struct DOps {
+  EvenOdd<T, N> fwd;  // out[j] = sum_m D[j][m] in[m]
+  EvenOdd<T, N> bwd;  // out[j] = sum_m D[m][j] in[m]
+};
+
+template <typename T, int N>
+void fill_even_odd(const double* D, bool transpose, EvenOdd<T, N>* eo) {
+  constexpr int H = N / 2;
+  auto at = [&](int j, int m) { return transpose ? D[m * N + j] : D[j * N + m]; };
+  for (int j = 0; j < H; ++j) {
+    for (int m = 0; m < H; ++m) {
+      eo->ae[j * H + m] = (T)(0.5 * (at(j, m) + at(j, N - 1 - m)));
+      eo->ao[j * H + m] = (T)(0.5 * (at(j, m) - at(j, N - 1 - m)));
+    }
+    eo->mid_col[j] = (N & 1) ? (T)at(j, H) : T(0);
+    eo->mid_row[j] = (N & 1) ? (T)at(H, j) : T(0);
+  }
+}
+
+// out = M in with M given by its even-odd factors.  `in` and `out` may alias
+// only if the caller copies; all indices are compile-time after unrolling.
+template <typename T, int N>
+__device__ __forceinline__ void eo_apply(const EvenOdd<T, N>& eo,
+                                         const T (&in)[N], T (&out)[N]) {
+  constexpr int H = N / 2;
+  if constexpr (H == 0) {
+    out[0] = T(0);
+    return;
+  }
+  T ce[H > 0 ? H : 1], co[H > 0 ? H : 1], E[H > 0 ? H : 1], O[H > 0 ? H : 1];
+#pragma unroll
+  for (int m = 0; m < H; ++m) {
+    ce[m] = in[m] + in[N - 1 - m];
+    co[m] = in[m] - in[N - 1 - m];
+  }
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    E[j] = (N & 1) ? eo.mid_col[j] * in[H] : T(0);
+    O[j] = T(0);
+  }
+#pragma unroll
+  for (int m = 0; m < H; ++m) {
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      E[j] += eo.ae[j * H + m] * ce[m];
+      O[j] += eo.ao[j * H + m] * co[m];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    out[j] = E[j] + O[j];
+    out[N - 1 - j] = O[j] - E[j];
+  }
+  if constexpr (N & 1) {
+    T acc = T(0);
+#pragma unroll
+    for (int m = 0; m < H; ++m) acc += eo.mid_row[m] * co[m];
+    out[H] = acc;
+  }
+}
+
+constexpr int pow2_at_least(int n) {
+  int r = 1;
+  while (r < n) r *= 2;
+  return r;
+}
 
 // EPB: elements per CTA; MINB: min CTAs per SM (register cap); KCH: slabs of
 // geometric factors loaded per batch in phase 3 (bounds registers in flight).
@@ -44,12 +123,12 @@ struct Cfg3DV2 {
   static constexpr int n = N * N * N;
   static constexpr int epb = EPB;
   static constexpr int threads = ((EPB * P + 31) / 32) * 32;
-  // padded strides: S1 odd; for 8-byte words consecutive a0 planes are offset
-  // by half the banks
-  static constexpr int S1 = (N % 2 == 0) ? N + 1 : N;
-  static constexpr int S0_raw = N * S1;
-  static constexpr int S0 =
-      sizeof(T) == 8 ? S0_raw + ((8 - (S0_raw % 16)) + 16) % 16 : S0_raw;
+  // swizzled tile: idx(a0,a1,a2) = a0*S0 + a1*R + (a2 ^ (a1 & (R-1))),
+  // R = row pitch (power of two), S0 == R (mod 2R) so that consecutive a0
+  // planes land on the other half of the banks.
+  static constexpr int R = pow2_at_least(N);
+  static constexpr int S0_raw = N * R;
+  static constexpr int S0 = S0_raw + ((R - (S0_raw % (2 * R))) + 2 * R) % (2 * R);
   static constexpr int tile = N * S0;
   static constexpr int tiles_per_slot = 4;  // u[2], A, B
   static constexpr int min_blocks = MINB;
@@ -78,17 +157,57 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH, int JU>
+// ---- bulk async copy (TMA 1-D, UBLKCP) + mbarrier, used to stage one
+//      element's geometric factors (a single contiguous chunk) in shared memory
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(s),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc,
+                                              unsigned bytes, uint64_t* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1], %2, [%3];" ::"r"(d),
+      "l"(gsrc), "r"(bytes), "r"(b)
+      : "memory");
+}
+
+template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH>
 __global__ void __launch_bounds__((Cfg3DV2<T, N, EPB, MINB, KCH>::threads),
                                   MINB)
-apply3d_v2_kernel(const __grid_constant__ DMat3<T, N> dm,
+apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
                   const uint32_t* __restrict__ conn,
                   const T* __restrict__ gf, T lambda, T mu,
                   const T* __restrict__ x, T* __restrict__ y, int ncomp,
                   int64_t E, double* __restrict__ dot_xy) {
   using C = Cfg3DV2<T, N, EPB, MINB, KCH>;
   constexpr int P = C::P, n = C::n, epb = C::epb;
-  constexpr int S0 = C::S0, S1 = C::S1;
+  constexpr int S0 = C::S0, R = C::R;
   constexpr int ngeom = MASS ? 7 : 6;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[32];
@@ -102,9 +221,11 @@ apply3d_v2_kernel(const __grid_constant__ DMat3<T, N> dm,
   T* sU0 = smem + (lane_ok ? slot : 0) * C::tiles_per_slot * C::tile;
   T* sA = sU0 + 2 * C::tile;
   T* sB = sA + C::tile;
-  const int offA = p * S1 + q;       // + k * S0      (mapping A)
-  const int offB = p * S0 + q;       // + m * S1      (mapping B)
-  const int offC = p * S0 + q * S1;  // + m           (mapping C)
+  // swizzled offsets (see Cfg3DV2)
+  const int offA = p * R + (q ^ (p & (R - 1)));  // + k * S0          mapping A
+  const int baseB = p * S0;                      // + m * R + (q ^ m)  mapping B
+  const int baseC = p * S0 + q * R;              // + (m ^ q)          mapping C
+  const int qs = q & (R - 1);
   const bool want_dot = !LOCAL && dot_xy != nullptr;
   double dot = 0.0;
 
@@ -113,6 +234,31 @@ apply3d_v2_kernel(const __grid_constant__ DMat3<T, N> dm,
   int64_t e = blk * epb + slot;
   bool active = lane_ok && blk < nblocks && e < E;
   uint32_t rc[N];
+
+  // KCH == 0: the element's geometric factors are staged in shared memory by
+  // one bulk async copy (TMA 1-D) per element, completion on an mbarrier
+  constexpr bool STAGE = KCH == 0;
+  constexpr unsigned gbytes = (unsigned)(ngeom * n * sizeof(T));
+  static_assert(!STAGE || gbytes % 16 == 0, "bulk copy needs 16 B multiples");
+  // (the CTA's `epb` elements are consecutive, so it is ONE copy per CTA step)
+  __shared__ __align__(8) uint64_t gbar;
+  T* sG0 = smem + epb * C::tiles_per_slot * C::tile;
+  T* sG = sG0 + (lane_ok ? slot : 0) * (ngeom * n);
+  unsigned gphase = 0;
+  auto stage_copy = [&](int64_t blk_id) {
+    // elected thread: refill the stage with the factors of CTA step `blk_id`
+    const int64_t first = blk_id * epb;
+    const int64_t count = (E - first) < epb ? (E - first) : epb;
+    const unsigned bytes = (unsigned)count * gbytes;
+    mbar_expect_tx(&gbar, bytes);
+    bulk_copy_g2s(sG0, gf + first * (int64_t)(ngeom * n), bytes, &gbar);
+  };
+  if (STAGE) {
+    if (threadIdx.x == 0) mbar_init(&gbar, 1);
+    mbar_fence_init();
+    __syncthreads();
+    if (threadIdx.x == 0 && blk < nblocks) stage_copy(blk);
+  }
 
   // prologue: gather of the first element into u tile 0
 #pragma unroll
@@ -151,12 +297,14 @@ apply3d_v2_kernel(const __grid_constant__ DMat3<T, N> dm,
 #pragma unroll
     for (int k = 0; k < N; ++k) nrc[k] = kConnSentinel;
     if (active_n) {
-      const char* g =
-          reinterpret_cast<const char*>(gf + e_n * (int64_t)(ngeom * n));
-      constexpr int lines = (ngeom * n * (int)sizeof(T) + 127) / 128;
+      if (!STAGE) {
+        const char* g =
+            reinterpret_cast<const char*>(gf + e_n * (int64_t)(ngeom * n));
+        constexpr int lines = (ngeom * n * (int)sizeof(T) + 127) / 128;
 #pragma unroll
-      for (int l = 0; l < (lines + P - 1) / P; ++l)
-        if (l * P + t < lines) prefetch_l2(g + (int64_t)(l * P + t) * 128);
+        for (int l = 0; l < (lines + P - 1) / P; ++l)
+          if (l * P + t < lines) prefetch_l2(g + (int64_t)(l * P + t) * 128);
+      }
       if (!LOCAL) {
 #pragma unroll
         for (int k = 0; k < N; ++k)
@@ -170,25 +318,17 @@ apply3d_v2_kernel(const __grid_constant__ DMat3<T, N> dm,
 
     // ---- phase 2 (mappings B, C): a1- and a2-derivatives
     if (lane_ok) {
-      T col[N];
+      T col[N], out[N];
 #pragma unroll
-      for (int m = 0; m < N; ++m) col[m] = sU[offB + m * S1];
-#pragma unroll(JU)
-      for (int j = 0; j < N; ++j) {
-        T acc = T(0);
+      for (int m = 0; m < N; ++m) col[m] = sU[baseB + m * R + (qs ^ m)];
+      eo_apply<T, N>(dm.fwd, col, out);
 #pragma unroll
-        for (int m = 0; m < N; ++m) acc += dm.d[j * N + m] * col[m];
-        sA[offB + j * S1] = acc;
-      }
+      for (int j = 0; j < N; ++j) sA[baseB + j * R + (qs ^ j)] = out[j];
 #pragma unroll
-      for (int m = 0; m < N; ++m) col[m] = sU[offC + m];
-#pragma unroll(JU)
-      for (int j = 0; j < N; ++j) {
-        T acc = T(0);
+      for (int m = 0; m < N; ++m) col[m] = sU[baseC + (m ^ qs)];
+      eo_apply<T, N>(dm.fwd, col, out);
 #pragma unroll
-        for (int m = 0; m < N; ++m) acc += dm.d[j * N + m] * col[m];
-        sB[offC + j] = acc;
-      }
+      for (int j = 0; j < N; ++j) sB[baseC + (j ^ qs)] = out[j];
     }
     __syncthreads();
 
@@ -218,35 +358,32 @@ apply3d_v2_kernel(const __grid_constant__ DMat3<T, N> dm,
 #pragma unroll
     for (int k = 0; k < N; ++k) ry[k] = T(0);
     if (lane_ok) {
-      T d0[N];
-      {
-        T col[N];
+      T d0[N], ucol[N];
 #pragma unroll
-        for (int m = 0; m < N; ++m) col[m] = sU[m * S0 + offA];
+      for (int m = 0; m < N; ++m) ucol[m] = sU[m * S0 + offA];
+      eo_apply<T, N>(dm.fwd, ucol, d0);
+      const T* g = STAGE ? sG + t
+                         : gf + (active ? e : 0) * (int64_t)(ngeom * n) + t;
+      if (STAGE) mbar_wait(&gbar, gphase);
+      constexpr int KB = STAGE ? 1 : (KCH > 0 ? KCH : 1);
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-          T acc = T(0);
+      for (int k0 = 0; k0 < N; k0 += KB) {
+        T gg[KB][7];
 #pragma unroll
-          for (int m = 0; m < N; ++m) acc += dm.d[k * N + m] * col[m];
-          d0[k] = acc;
-          if (MASS) ry[k] = col[k];  // u, scaled by lambda W detJ below
-        }
-      }
-      const T* g = gf + (active ? e : 0) * (int64_t)(ngeom * n) + t;
-#pragma unroll
-      for (int k0 = 0; k0 < N; k0 += KCH) {
-        T gg[KCH][7];
-#pragma unroll
-        for (int kk = 0; kk < KCH; ++kk) {
+        for (int kk = 0; kk < KB; ++kk) {
           const int k = k0 + kk;
           if (k < N) {
 #pragma unroll
-            for (int s = 0; s < ngeom; ++s)
-              gg[kk][s] = active ? ld_stream(g + k * P + s * n) : T(0);
+            for (int s = 0; s < ngeom; ++s) {
+              if (STAGE)
+                gg[kk][s] = active ? g[k * P + s * n] : T(0);
+              else
+                gg[kk][s] = active ? ld_stream(g + k * P + s * n) : T(0);
+            }
           }
         }
 #pragma unroll
-        for (int kk = 0; kk < KCH; ++kk) {
+        for (int kk = 0; kk < KB; ++kk) {
           const int k = k0 + kk;
           if (k < N) {
             const T d1 = sA[k * S0 + offA];
@@ -258,43 +395,40 @@ apply3d_v2_kernel(const __grid_constant__ DMat3<T, N> dm,
             sB[k * S0 + offA] = mu * (gg[kk][2] * d0[k] + gg[kk][4] * d1 +
                                       gg[kk][5] * d2);
             d0[k] = w0;
-            if (MASS) ry[k] *= lambda * gg[kk][6];
+            if (MASS) ucol[k] *= lambda * gg[kk][6];
           }
         }
         // keep the compiler from hoisting every slab's loads to the top
-        asm volatile("" ::: "memory");
+        if (!STAGE) asm volatile("" ::: "memory");
       }
+      eo_apply<T, N>(dm.bwd, d0, ry);
+      if (MASS) {
 #pragma unroll
-      for (int m = 0; m < N; ++m) {
-        T acc = ry[m];
-#pragma unroll
-        for (int k = 0; k < N; ++k) acc += dm.d[k * N + m] * d0[k];
-        ry[m] = acc;
+        for (int k = 0; k < N; ++k) ry[k] += ucol[k];
       }
     }
     __syncthreads();
+    if (STAGE) {
+      // every thread of the slot is done reading the staged factors: refill
+      // the stage with the next element's chunk (lands during phases 4, 5 and
+      // the next element's phase 2)
+      gphase ^= 1;
+      if (threadIdx.x == 0 && blk_n < nblocks) stage_copy(blk_n);
+    }
 
     // ---- phase 4 (mappings B, C): transposed a1-, a2-derivatives, in place
     if (lane_ok) {
-      T col[N];
+      T col[N], out[N];
 #pragma unroll
-      for (int m = 0; m < N; ++m) col[m] = sA[offB + m * S1];
-#pragma unroll(JU)
-      for (int j = 0; j < N; ++j) {
-        T acc = T(0);
+      for (int m = 0; m < N; ++m) col[m] = sA[baseB + m * R + (qs ^ m)];
+      eo_apply<T, N>(dm.bwd, col, out);
 #pragma unroll
-        for (int m = 0; m < N; ++m) acc += dm.d[m * N + j] * col[m];
-        sA[offB + j * S1] = acc;
-      }
+      for (int j = 0; j < N; ++j) sA[baseB + j * R + (qs ^ j)] = out[j];
 #pragma unroll
-      for (int m = 0; m < N; ++m) col[m] = sB[offC + m];
-#pragma unroll(JU)
-      for (int j = 0; j < N; ++j) {
-        T acc = T(0);
+      for (int m = 0; m < N; ++m) col[m] = sB[baseC + (m ^ qs)];
+      eo_apply<T, N>(dm.bwd, col, out);
 #pragma unroll
-        for (int m = 0; m < N; ++m) acc += dm.d[m * N + j] * col[m];
-        sB[offC + j] = acc;
-      }
+      for (int j = 0; j < N; ++j) sB[baseC + (j ^ qs)] = out[j];
     }
     __syncthreads();
 
@@ -338,15 +472,17 @@ apply3d_v2_kernel(const __grid_constant__ DMat3<T, N> dm,
   }
 }
 
-template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH, int JU>
+template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH>
 int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
                     void* y, int ncomp, double* dot_xy, cudaStream_t stream) {
   using C = Cfg3DV2<T, N, EPB, MINB, KCH>;
   const int64_t E = op.base.desc.num_elements;
   const int64_t nblocks = (E + C::epb - 1) / C::epb;
   const size_t smem =
-      (size_t)C::epb * C::tiles_per_slot * C::tile * sizeof(T);
-  auto kernel = apply3d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB, KCH, JU>;
+      (size_t)C::epb *
+      (C::tiles_per_slot * C::tile + (KCH == 0 ? (MASS ? 7 : 6) * C::n : 0)) *
+      sizeof(T);
+  auto kernel = apply3d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB, KCH>;
   static int per_sm = 0;
   if (per_sm == 0) {
     if (smem > 48 * 1024)
@@ -359,8 +495,9 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
   // persistent CTAs: one wave, every CTA pipelines over its elements
   const int64_t cap = (int64_t)num_sms() * per_sm;
   dim3 grid((unsigned)(nblocks < cap ? nblocks : cap), ncomp);
-  DMat3<T, N> dm;
-  for (int i = 0; i < N * N; ++i) dm.d[i] = (T)op.base.h_BD[i];
+  DOps<T, N> dm;
+  fill_even_odd<T, N>(op.base.h_BD, false, &dm.fwd);
+  fill_even_odd<T, N>(op.base.h_BD, true, &dm.bwd);
   kernel<<<grid, C::threads, smem, stream>>>(
       dm, op.conn, (const T*)op.geom, (T)lambda, (T)mu, (const T*)x, (T*)y,
       ncomp, E, dot_xy);
@@ -377,36 +514,60 @@ int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
   if constexpr (N == 8 && !MASS && !LOCAL) {
     switch (op.variant) {
       case 3:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 4, 1, 2, 8>(
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, 1, 5, 0>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
       case 4:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 2, 3, 2, 8>(
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, 1, 4, 0>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
       case 5:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 4, 2, 2, 2>(
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, 2, 2, 0>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
       case 6:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 4, 2, 2, 1>(
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, 1, 8, 2>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
       case 7:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 4, 2, 4, 2>(
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, 1, 3, 0>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
       case 8:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 2, 4, 2, 2>(
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, 2, 3, 0>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
       case 9:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 4, 2, 2, 4>(
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, 1, 6, 0>(
+            op, lambda, mu, x, y, ncomp, dot_xy, stream);
+      case 10:
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, 4, 1, 0>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
       default:
         break;
     }
   }
 #endif
-  constexpr int MINB = (N <= 8) ? 2 : 1;
-  // fp64 contractions fetch every D entry through a uniform register: full
-  // unrolling of the output index spills, so fp64 unrolls by 2
-  constexpr int JU = sizeof(T) == 8 ? 2 : N;
-  return launch3d_v2_cfg<T, N, MASS, LOCAL, E0, MINB, 2, JU>(
+  (void)E0;
+  // Default configuration: small CTAs (>= 64 threads fp64, >= 128 fp32), the
+  // geometric factors staged through shared memory by bulk async copies
+  // whenever the CTA's tiles + stage fit; the number of resident CTAs follows
+  // from the shared-memory footprint and a register estimate.
+  constexpr int P = N * N;
+  constexpr int target = sizeof(T) == 8 ? 64 : 128;
+  constexpr int epb0 = (target + P - 1) / P;
+  constexpr int EPB = epb0 < 1 ? 1 : (epb0 > 16 ? 16 : epb0);
+  using C0 = Cfg3DV2<T, N, EPB, 1, 0>;
+  constexpr long stage_bytes =
+      (long)EPB * (C0::tiles_per_slot * C0::tile + (MASS ? 7 : 6) * C0::n) *
+      (long)sizeof(T);
+  constexpr bool staged =
+      stage_bytes <= 200 * 1024 && (((MASS ? 7 : 6) * C0::n * sizeof(T)) % 16) == 0;
+  constexpr int KCH = staged ? 0 : 2;
+  constexpr long smem_bytes =
+      staged ? stage_bytes
+             : (long)EPB * C0::tiles_per_slot * C0::tile * (long)sizeof(T);
+  constexpr int by_smem = (int)((220L * 1024) / (smem_bytes > 0 ? smem_bytes : 1));
+  constexpr int est_regs_raw = 40 + (sizeof(T) == 8 ? 18 : 9) * N;
+  constexpr int est_regs = est_regs_raw > 255 ? 255 : est_regs_raw;
+  constexpr int by_regs = 65536 / (C0::threads * est_regs);
+  constexpr int m0 = by_smem < by_regs ? by_smem : by_regs;
+  constexpr int MINB = m0 < 1 ? 1 : (m0 > 8 ? 8 : m0);
+  return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, MINB, KCH>(
       op, lambda, mu, x, y, ncomp, dot_xy, stream);
 }
 
