@@ -183,6 +183,17 @@ void sfem_op_destroy(sfem_op* op);
 int sfem_op_apply(const sfem_op* op, double lambda, double mu, const void* x,
                   void* y, int32_t ncomp, void* dot_xy, sfem_stream_t stream);
 
+/* Same operator restricted to the elements [elem_begin, elem_end) (elem_begin
+ * a multiple of 4).  `first` != 0: zero the shared-dof prefix of y and dot_xy
+ * before accumulating; later calls on the same y pass first = 0.  Used to
+ * overlap the halo exchange of a partitioned mesh with interior compute: the
+ * rank's interface elements are stored first, applied first, their shared
+ * dofs are packed and sent while the interior elements are applied. */
+int sfem_op_apply_range(const sfem_op* op, double lambda, double mu,
+                        const void* x, void* y, int32_t ncomp,
+                        int64_t elem_begin, int64_t elem_end, int32_t first,
+                        void* dot_xy, sfem_stream_t stream);
+
 /* Local (E-vector) form: y_local = local_covector(form, (u_local, v)).
  * u_local, y_local: (E, N^d, ncomp). */
 int sfem_op_apply_local(const sfem_op* op, double lambda, double mu,
@@ -226,6 +237,34 @@ int64_t sfem_cg_workspace_bytes(int dtype, int64_t size);
 int sfem_cg(const sfem_op* op, const void* b, void* x, int32_t ncomp,
             const void* minv, const sfem_cg_params* params, void* workspace,
             sfem_cg_info* info, sfem_stream_t stream);
+
+/* Building blocks of the same fused CG for hosts that interleave collectives
+ * (one process per GPU: halo exchange after the apply, NCCL all-reduce of the
+ * two scalars).  `state`: device buffer of sfem_cg_state_bytes() bytes whose
+ * first four doubles are [0] p.Ap (written by sfem_op_apply's dot_xy),
+ * [1] gamma_new, [2] gamma, [3] b.b -- the values a distributed host
+ * all-reduces.  `owned`: device uint8 (n), 1 where this rank counts the dof in
+ * dot products (NULL: all).  No call synchronises the host except
+ * sfem_cg_read.  Order per solve:
+ *   Ax = A x0 (+ exchange); sfem_cg_init; [allreduce state[2..3]];
+ *   sfem_cg_init_finish; then per iteration: apply(p -> Ap, dot_xy = &state[0])
+ *   (+ exchange) [allreduce state[0]]; sfem_cg_update [allreduce state[1]];
+ *   sfem_cg_direction; sfem_cg_advance.  Kernels are no-ops once converged. */
+int64_t sfem_cg_state_bytes(void);
+int sfem_cg_init(int dtype, int64_t n, const void* b, const void* Ax,
+                 const void* minv, const uint8_t* owned, void* r, void* p,
+                 void* state, double tol, double atol, int64_t maxiter,
+                 sfem_stream_t stream);
+int sfem_cg_init_finish(void* state, sfem_stream_t stream);
+int sfem_cg_update(int dtype, int64_t n, void* x, void* r, const void* p,
+                   const void* Ap, const void* minv, const uint8_t* owned,
+                   void* state, sfem_stream_t stream);
+int sfem_cg_direction(int dtype, int64_t n, const void* r, void* p,
+                      const void* minv, void* state, sfem_stream_t stream);
+int sfem_cg_advance(void* state, sfem_stream_t stream);
+/* Copies the state to the host (synchronises the stream). */
+int sfem_cg_read(const void* state, sfem_cg_info* info, int32_t* done,
+                 sfem_stream_t stream);
 
 /* Fused vector kernels for the generic (callable-A) CG path.  All device. */
 /* y = a*x + b*y */

@@ -94,6 +94,9 @@ SIGNATURES = {
     'sfem_op_destroy': (None, [_c_ptr]),
     'sfem_op_apply': (ctypes.c_int, [_c_ptr, _c_f64, _c_f64, _c_ptr, _c_ptr,
                                      _c_i32, _c_ptr, _c_ptr]),
+    'sfem_op_apply_range': (ctypes.c_int, [_c_ptr, _c_f64, _c_f64, _c_ptr,
+                                           _c_ptr, _c_i32, _c_i64, _c_i64,
+                                           _c_i32, _c_ptr, _c_ptr]),
     'sfem_op_apply_local': (ctypes.c_int, [_c_ptr, _c_f64, _c_f64, _c_ptr,
                                            _c_ptr, _c_i32, _c_ptr]),
     'sfem_op_diag': (ctypes.c_int, [_c_ptr, _c_f64, _c_f64, _c_ptr, _c_ptr]),
@@ -102,6 +105,19 @@ SIGNATURES = {
     'sfem_cg': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr,
                                ctypes.POINTER(CgParams), _c_ptr,
                                ctypes.POINTER(CgInfo), _c_ptr]),
+    'sfem_cg_state_bytes': (_c_i64, []),
+    'sfem_cg_init': (ctypes.c_int, [ctypes.c_int, _c_i64, _c_ptr, _c_ptr,
+                                    _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr,
+                                    _c_f64, _c_f64, _c_i64, _c_ptr]),
+    'sfem_cg_init_finish': (ctypes.c_int, [_c_ptr, _c_ptr]),
+    'sfem_cg_update': (ctypes.c_int, [ctypes.c_int, _c_i64, _c_ptr, _c_ptr,
+                                      _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr,
+                                      _c_ptr]),
+    'sfem_cg_direction': (ctypes.c_int, [ctypes.c_int, _c_i64, _c_ptr, _c_ptr,
+                                         _c_ptr, _c_ptr, _c_ptr]),
+    'sfem_cg_advance': (ctypes.c_int, [_c_ptr, _c_ptr]),
+    'sfem_cg_read': (ctypes.c_int, [_c_ptr, ctypes.POINTER(CgInfo),
+                                    ctypes.POINTER(_c_i32), _c_ptr]),
     'sfem_axpby': (ctypes.c_int, [ctypes.c_int, _c_i64, _c_f64, _c_ptr, _c_f64,
                                   _c_ptr, _c_ptr]),
     'sfem_dot': (ctypes.c_int, [ctypes.c_int, _c_i64, _c_ptr, _c_ptr, _c_ptr,

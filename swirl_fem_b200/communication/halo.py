@@ -101,25 +101,71 @@ class HaloPlan:
   def _unpack_add(self, u, idx, buf):
     _lib.halo_unpack_add(u, idx, buf)
 
+  def _flat_lists(self, device, dtype):
+    """Concatenated (all peers) index list, buffers and split sizes."""
+    key = ('flat', str(device), dtype)
+    if key not in self._dev:
+      splits = [len(self.local_idx[q]) if q in self.local_idx else 0
+                for q in range(self.world)]
+      cat = (np.concatenate([self.local_idx[q] for q in self.peers])
+             if self.peers else np.zeros(0, np.int32))
+      idx = torch.as_tensor(cat.astype(np.int32)).to(device)
+      send = torch.empty(len(cat), dtype=dtype, device=device)
+      recv = torch.empty(len(cat), dtype=dtype, device=device)
+      offs = np.concatenate([[0], np.cumsum(splits)])
+      self._dev[key] = (idx, send, recv, splits, offs)
+    return self._dev[key]
+
   def exchange_(self, u: torch.Tensor) -> torch.Tensor:
-    """In-place QQ^T on this rank's `(num_local_nodes,)` vector."""
+    """In-place QQ^T on this rank's `(num_local_nodes,)` vector.
+
+    One pack kernel for all peers, ONE `all_to_all_single` (NCCL grouped
+    send/recv; the host never blocks), then one unpack-add kernel per peer in
+    ascending peer order (a dof shared with several peers occurs once per
+    peer, so the adds of different peers must not race).
+    """
     import torch.distributed as dist  # pylint: disable=g-import-not-at-top
     if not self.peers:
       return u
-    idx, send, recv = self._device_lists(u.device, u.dtype)
-    ops = []
+    idx, send, recv, splits, offs = self._flat_lists(u.device, u.dtype)
+    self._pack(u, idx, send)
+    dist.all_to_all_single(recv, send, output_split_sizes=splits,
+                           input_split_sizes=splits, group=self.group)
     for q in self.peers:
-      self._pack(u, idx[q], send[q])
-      ops.append(dist.P2POp(dist.isend, send[q], q, group=self.group))
-      ops.append(dist.P2POp(dist.irecv, recv[q], q, group=self.group))
-    for work in dist.batch_isend_irecv(ops):
-      work.wait()
+      lo, hi = int(offs[q]), int(offs[q + 1])
+      self._unpack_add(u, idx[lo:hi], recv[lo:hi])
+    return u
+
+  # -- split form, used to overlap the wire time with interior compute -------
+  def side_stream(self, device):
+    key = ('stream', str(device))
+    if key not in self._dev:
+      self._dev[key] = torch.cuda.Stream(device=device)
+    return self._dev[key]
+
+  def start_exchange(self, u: torch.Tensor):
+    """Pack + all_to_all on the CURRENT stream (call it on a side stream)."""
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    idx, send, recv, splits, _ = self._flat_lists(u.device, u.dtype)
+    self._pack(u, idx, send)
+    dist.all_to_all_single(recv, send, output_split_sizes=splits,
+                           input_split_sizes=splits, group=self.group)
+
+  def finish_exchange(self, u: torch.Tensor):
+    """Unpack-add of the received values (after `start_exchange` completed)."""
+    idx, _, recv, _, offs = self._flat_lists(u.device, u.dtype)
     for q in self.peers:
-      self._unpack_add(u, idx[q], recv[q])
+      lo, hi = int(offs[q]), int(offs[q + 1])
+      self._unpack_add(u, idx[lo:hi], recv[lo:hi])
     return u
 
   def exchange(self, u: torch.Tensor) -> torch.Tensor:
     return self.exchange_(u.contiguous().clone())
 
-  def owned_mask(self, device, dtype) -> torch.Tensor:
-    return torch.as_tensor(self.owned).to(device=device, dtype=dtype)
+  def owned_mask(self, device, dtype=torch.uint8) -> torch.Tensor:
+    """Device copy of `owned` (cached: it is read by every CG update)."""
+    key = ('owned', str(device), dtype)
+    if key not in self._dev:
+      self._dev[key] = torch.as_tensor(self.owned).to(
+          device=device, dtype=dtype).contiguous()
+    return self._dev[key]

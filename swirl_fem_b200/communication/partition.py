@@ -39,6 +39,7 @@ class BlockPartition:
   num_global_dofs: int
   block_index: tuple
   grid: tuple
+  num_interface_elements: int = 0  # leading elements that touch other ranks
 
 
 def block_partition(ne: int, ndim: int, gridpoints_1d: Nodes1D, rank: int,
@@ -102,11 +103,30 @@ def block_partition(ne: int, ndim: int, gridpoints_1d: Nodes1D, rank: int,
   else:
     loc = np.zeros(0, dtype=np.int64)
     gid = np.zeros(0, dtype=np.int64)
+  # Element order: the elements touching another rank's block come first (their
+  # number rounded up to a multiple of 4 with interior elements), so that the
+  # halo exchange can start after a launch over `[0, num_interface_elements)`
+  # and overlap with the launch over the interior elements.
+  touches = np.zeros(nloc, dtype=bool)
+  for axis in range(ndim):
+    for side in (0, 1):
+      on_global_boundary = (bidx[axis] == 0 if side == 0
+                            else bidx[axis] == grid[axis] - 1)
+      if on_global_boundary:
+        continue
+      sl = [slice(None)] * ndim
+      sl[axis] = 0 if side == 0 else nloc[axis] - 1
+      touches[tuple(sl)] = True
+  touches = touches.reshape(-1)
+  order = np.concatenate([np.nonzero(touches)[0], np.nonzero(~touches)[0]])
+  num_interface = int(touches.sum())
+  num_interface = min(len(order), -(-num_interface // 4) * 4)
+  refined = refined.replace(elements=refined.elements[order])
   return BlockPartition(
       premesh=refined, dirichlet=dirichlet,
       interface_local=loc.astype(np.int32), interface_global=gid,
       num_global_dofs=lattice ** ndim, block_index=tuple(int(i) for i in bidx),
-      grid=grid)
+      grid=grid, num_interface_elements=num_interface)
 
 
 def halo_plan_from_interfaces(rank: int, interface_local: np.ndarray,

@@ -112,6 +112,48 @@ class FusedOperator:
                   'sfem_op_apply')
     return y
 
+  def apply_range(self, x: torch.Tensor, out: torch.Tensor, elem_begin: int,
+                  elem_end: int, first: bool, lam: float = 0.0,
+                  mu: float = 1.0, dot_out: torch.Tensor | None = None):
+    """Accumulates the contribution of elements `[elem_begin, elem_end)`."""
+    _lib.require_cuda(x, out)
+    assert x.is_contiguous() and out.is_contiguous() and x.dtype == self.dtype
+    with torch.cuda.device(x.device):
+      _lib._check(_lib.lib().sfem_op_apply_range(
+          self.handle, float(lam), float(mu), _lib.ptr(x), _lib.ptr(out),
+          self._ncomp(x), int(elem_begin), int(elem_end), int(bool(first)),
+          _lib.ptr(dot_out), _lib.stream_ptr(x.device)), 'sfem_op_apply_range')
+    return out
+
+  def apply_partitioned(self, x: torch.Tensor, out: torch.Tensor, halo,
+                        num_interface_elements: int, lam: float = 0.0,
+                        mu: float = 1.0, dot_out: torch.Tensor | None = None):
+    """Partitioned apply with the halo exchange overlapped with interior work.
+
+    Elements `[0, num_interface_elements)` are the ones touching another
+    rank's block (`communication.partition` stores them first).  Their result
+    is complete on the shared dofs after the first launch, so those dofs are
+    packed and sent on a side stream while the interior elements run.
+    """
+    ne = self.mesh.num_elements
+    ni = int(num_interface_elements)
+    if halo is None or not halo.peers:
+      return self.apply(x, lam=lam, mu=mu, out=out, dot_out=dot_out)
+    main = torch.cuda.current_stream(x.device)
+    side = halo.side_stream(x.device)
+    self.apply_range(x, out, 0, ni, True, lam, mu, dot_out)
+    ready = torch.cuda.Event()
+    ready.record(main)
+    side.wait_event(ready)
+    with torch.cuda.stream(side):
+      halo.start_exchange(out)          # pack + all_to_all on the side stream
+      sent = torch.cuda.Event()
+      sent.record(side)
+    self.apply_range(x, out, ni, ne, False, lam, mu, dot_out)
+    main.wait_event(sent)
+    halo.finish_exchange(out)           # unpack-add on the main stream
+    return out
+
   def apply_local(self, u_local: torch.Tensor, lam: float = 0.0,
                   mu: float = 1.0, ncomp: int = 1) -> torch.Tensor:
     """E-vector form: `(E, n[, ncomp]) -> (E, n[, ncomp])`."""

@@ -216,12 +216,14 @@ int64_t sfem_op_geom_bytes(const sfem_space_desc* desc, int32_t with_mass) {
   if (!desc || desc->dim < 1 || desc->dim > 3) return -1;
   const int64_t q = sfem::ipow(desc->q1d, desc->dim);
   const int64_t esz = desc->dtype == SFEM_F64 ? 8 : 4;
-  return desc->num_elements * q * sfem::ngeom_of(*desc, with_mass) * esz;
+  // + 64 B: bulk async copies round a CTA step's chunk up to 16 bytes
+  return desc->num_elements * q * sfem::ngeom_of(*desc, with_mass) * esz + 64;
 }
 
 int64_t sfem_op_conn_bytes(const sfem_space_desc* desc) {
   if (!desc || desc->dim < 1 || desc->dim > 3) return -1;
-  return desc->num_elements * (int64_t)sfem::ipow(desc->n1d, desc->dim) * 4;
+  return desc->num_elements * (int64_t)sfem::ipow(desc->n1d, desc->dim) * 4 +
+         64;
 }
 
 int sfem_op_create(const sfem_space_desc* desc, const uint8_t* dirichlet,
@@ -284,6 +286,45 @@ int sfem_op_apply(const sfem_op* op, double lambda, double mu, const void* x,
   SFEM_REQUIRE(ncomp >= 1 && ncomp <= 65535, "bad ncomp");
   return op_apply_internal(op, lambda, mu, x, y, ncomp, (double*)dot_xy,
                            (cudaStream_t)stream);
+}
+
+int sfem_op_apply_range(const sfem_op* op, double lambda, double mu,
+                        const void* x, void* y, int32_t ncomp,
+                        int64_t elem_begin, int64_t elem_end, int32_t first,
+                        void* dot_xy, sfem_stream_t stream_) {
+  using namespace sfem;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SFEM_REQUIRE(op && x && y, "null argument");
+  SFEM_REQUIRE(x != y, "sfem_op_apply_range is out of place");
+  SFEM_REQUIRE(ncomp >= 1 && ncomp <= 65535, "bad ncomp");
+  const sfem_space_desc& d = op->base.desc;
+  SFEM_REQUIRE(elem_begin >= 0 && elem_begin <= elem_end &&
+                   elem_end <= d.num_elements,
+               "element range out of bounds");
+  SFEM_REQUIRE(elem_begin % 4 == 0,
+               "elem_begin must be a multiple of 4 (16-byte aligned chunks)");
+  SFEM_REQUIRE(lambda == 0.0 || op->with_mass,
+               "operator was created without mass factors but lambda != 0");
+  const size_t esz = d.dtype == SFEM_F64 ? 8 : 4;
+  if (first) {
+    if (op->n_zero > 0)
+      SFEM_CUDA_CHECK(cudaMemsetAsync(y, 0, esz * (size_t)op->n_zero * ncomp,
+                                      stream));
+    if (dot_xy)
+      SFEM_CUDA_CHECK(cudaMemsetAsync(dot_xy, 0, sizeof(double), stream));
+  }
+  if (elem_begin == elem_end) return SFEM_OK;
+  // a shallow view of the handle restricted to [elem_begin, elem_end)
+  sfem_op sub = *op;
+  sub.conn = op->conn + elem_begin * (int64_t)op->base.n;
+  sub.geom = (char*)op->geom +
+             (size_t)elem_begin * op->ngeom * op->base.q * esz;
+  sub.base.desc.num_elements = elem_end - elem_begin;
+  return d.dtype == SFEM_F64
+             ? apply_dispatch<double>(sub, lambda, mu, x, y, ncomp, false,
+                                      (double*)dot_xy, stream)
+             : apply_dispatch<float>(sub, lambda, mu, x, y, ncomp, false,
+                                     (double*)dot_xy, stream);
 }
 
 int sfem_op_apply_local(const sfem_op* op, double lambda, double mu,

@@ -32,6 +32,7 @@
 #pragma once
 
 #include "sfem_common.cuh"
+#include "sfem_tile_layouts.cuh"
 
 namespace sfem {
 namespace {
@@ -123,14 +124,24 @@ struct Cfg3DV2 {
   static constexpr int n = N * N * N;
   static constexpr int epb = EPB;
   static constexpr int threads = ((EPB * P + 31) / 32) * 32;
-  // swizzled tile: idx(a0,a1,a2) = a0*S0 + a1*R + (a2 ^ (a1 & (R-1))),
-  // R = row pitch (power of two), S0 == R (mod 2R) so that consecutive a0
-  // planes land on the other half of the banks.
-  static constexpr int R = pow2_at_least(N);
-  static constexpr int S0_raw = N * R;
-  static constexpr int S0 = S0_raw + ((R - (S0_raw % (2 * R))) + 2 * R) % (2 * R);
+  // tile index: idx(a0,a1,a2) = a0*S0 + a1*R + (SWZ ? a2 ^ a1 : a2).  The
+  // pitches (and whether the XOR swizzle is used: power-of-two N only) come
+  // from an offline search that minimises shared-memory wavefronts over the
+  // three access patterns for the actual lane -> (p, q) assignment
+  // (tools/tile_layout_search.py -> sfem_tile_layouts.cuh).
+  static constexpr int R = (sizeof(T) == 8 ? kTileLayout64 : kTileLayout32)[N][0];
+  static constexpr int S0 = (sizeof(T) == 8 ? kTileLayout64 : kTileLayout32)[N][1];
+  static constexpr bool SWZ =
+      (sizeof(T) == 8 ? kTileLayout64 : kTileLayout32)[N][2] != 0;
+  static constexpr int slot_pad =
+      (sizeof(T) == 8 ? kTileLayout64 : kTileLayout32)[N][3];
   static constexpr int tile = N * S0;
   static constexpr int tiles_per_slot = 4;  // u[2], A, B
+  static constexpr int slot_stride = tiles_per_slot * tile + slot_pad;
+  // offset (in T) of the factor stage: 16-byte aligned
+  static constexpr int stage_off(int epb_) {
+    return ((epb_ * slot_stride * (int)sizeof(T) + 15) / 16) * 16 / (int)sizeof(T);
+  }
   static constexpr int min_blocks = MINB;
   static constexpr int kch = KCH;
 };
@@ -208,6 +219,7 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
   using C = Cfg3DV2<T, N, EPB, MINB, KCH>;
   constexpr int P = C::P, n = C::n, epb = C::epb;
   constexpr int S0 = C::S0, R = C::R;
+  constexpr bool SWZ = C::SWZ;
   constexpr int ngeom = MASS ? 7 : 6;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[32];
@@ -218,14 +230,14 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
   const int p = t / N, q = t - p * N;
   const int c = blockIdx.y;
   const bool lane_ok = slot < epb;
-  T* sU0 = smem + (lane_ok ? slot : 0) * C::tiles_per_slot * C::tile;
+  T* sU0 = smem + (lane_ok ? slot : 0) * C::slot_stride;
   T* sA = sU0 + 2 * C::tile;
   T* sB = sA + C::tile;
   // swizzled offsets (see Cfg3DV2)
-  const int offA = p * R + (q ^ (p & (R - 1)));  // + k * S0          mapping A
-  const int baseB = p * S0;                      // + m * R + (q ^ m)  mapping B
-  const int baseC = p * S0 + q * R;              // + (m ^ q)          mapping C
-  const int qs = q & (R - 1);
+  const int offA = p * R + (SWZ ? (q ^ p) : q);  // + k * S0          mapping A
+  const int baseB = p * S0;                      // + m * R + sw(q, m) mapping B
+  const int baseC = p * S0 + q * R;              // + sw(m, q)         mapping C
+  const int qs = q;
   const bool want_dot = !LOCAL && dot_xy != nullptr;
   double dot = 0.0;
 
@@ -242,7 +254,7 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
   static_assert(!STAGE || gbytes % 16 == 0, "bulk copy needs 16 B multiples");
   // (the CTA's `epb` elements are consecutive, so it is ONE copy per CTA step)
   __shared__ __align__(8) uint64_t gbar;
-  T* sG0 = smem + epb * C::tiles_per_slot * C::tile;
+  T* sG0 = smem + C::stage_off(epb);
   T* sG = sG0 + (lane_ok ? slot : 0) * (ngeom * n);
   unsigned gphase = 0;
   auto stage_copy = [&](int64_t blk_id) {
@@ -320,15 +332,15 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     if (lane_ok) {
       T col[N], out[N];
 #pragma unroll
-      for (int m = 0; m < N; ++m) col[m] = sU[baseB + m * R + (qs ^ m)];
+      for (int m = 0; m < N; ++m) col[m] = sU[baseB + m * R + (SWZ ? (qs ^ m) : qs)];
       eo_apply<T, N>(dm.fwd, col, out);
 #pragma unroll
-      for (int j = 0; j < N; ++j) sA[baseB + j * R + (qs ^ j)] = out[j];
+      for (int j = 0; j < N; ++j) sA[baseB + j * R + (SWZ ? (qs ^ j) : qs)] = out[j];
 #pragma unroll
-      for (int m = 0; m < N; ++m) col[m] = sU[baseC + (m ^ qs)];
+      for (int m = 0; m < N; ++m) col[m] = sU[baseC + (SWZ ? (m ^ qs) : m)];
       eo_apply<T, N>(dm.fwd, col, out);
 #pragma unroll
-      for (int j = 0; j < N; ++j) sB[baseC + (j ^ qs)] = out[j];
+      for (int j = 0; j < N; ++j) sB[baseC + (SWZ ? (j ^ qs) : j)] = out[j];
     }
     __syncthreads();
 
@@ -420,15 +432,15 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     if (lane_ok) {
       T col[N], out[N];
 #pragma unroll
-      for (int m = 0; m < N; ++m) col[m] = sA[baseB + m * R + (qs ^ m)];
+      for (int m = 0; m < N; ++m) col[m] = sA[baseB + m * R + (SWZ ? (qs ^ m) : qs)];
       eo_apply<T, N>(dm.bwd, col, out);
 #pragma unroll
-      for (int j = 0; j < N; ++j) sA[baseB + j * R + (qs ^ j)] = out[j];
+      for (int j = 0; j < N; ++j) sA[baseB + j * R + (SWZ ? (qs ^ j) : qs)] = out[j];
 #pragma unroll
-      for (int m = 0; m < N; ++m) col[m] = sB[baseC + (m ^ qs)];
+      for (int m = 0; m < N; ++m) col[m] = sB[baseC + (SWZ ? (m ^ qs) : m)];
       eo_apply<T, N>(dm.bwd, col, out);
 #pragma unroll
-      for (int j = 0; j < N; ++j) sB[baseC + (j ^ qs)] = out[j];
+      for (int j = 0; j < N; ++j) sB[baseC + (SWZ ? (j ^ qs) : j)] = out[j];
     }
     __syncthreads();
 
@@ -479,8 +491,8 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
   const int64_t E = op.base.desc.num_elements;
   const int64_t nblocks = (E + C::epb - 1) / C::epb;
   const size_t smem =
-      (size_t)C::epb *
-      (C::tiles_per_slot * C::tile + (KCH == 0 ? (MASS ? 7 : 6) * C::n : 0)) *
+      ((size_t)C::stage_off(C::epb) +
+       (KCH == 0 ? (size_t)C::epb * (MASS ? 7 : 6) * C::n : 0)) *
       sizeof(T);
   auto kernel = apply3d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB, KCH>;
   static int per_sm = 0;
@@ -553,14 +565,13 @@ int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
   constexpr int EPB = epb0 < 1 ? 1 : (epb0 > 16 ? 16 : epb0);
   using C0 = Cfg3DV2<T, N, EPB, 1, 0>;
   constexpr long stage_bytes =
-      (long)EPB * (C0::tiles_per_slot * C0::tile + (MASS ? 7 : 6) * C0::n) *
+      ((long)C0::stage_off(EPB) + (long)EPB * (MASS ? 7 : 6) * C0::n) *
       (long)sizeof(T);
   constexpr bool staged =
       stage_bytes <= 200 * 1024 && (((MASS ? 7 : 6) * C0::n * sizeof(T)) % 16) == 0;
   constexpr int KCH = staged ? 0 : 2;
   constexpr long smem_bytes =
-      staged ? stage_bytes
-             : (long)EPB * C0::tiles_per_slot * C0::tile * (long)sizeof(T);
+      staged ? stage_bytes : (long)C0::stage_off(EPB) * (long)sizeof(T);
   constexpr int by_smem = (int)((220L * 1024) / (smem_bytes > 0 ? smem_bytes : 1));
   constexpr int est_regs_raw = 40 + (sizeof(T) == 8 ? 18 : 9) * N;
   constexpr int est_regs = est_regs_raw > 255 ? 255 : est_regs_raw;

@@ -117,6 +117,14 @@ def _worker_block(rank, world, port, ndim, ne, n1d):
     assert (mult[interior] == 1).all()
     assert (mult[blk.interface_local] >= 2).all()
     assert mult.max() <= 2 ** ndim
+    # elements that touch an interface dof are stored first (overlap split)
+    is_iface = np.zeros(len(f), dtype=bool)
+    is_iface[blk.interface_local] = True
+    touching = is_iface[blk.premesh.elements].any(axis=1)
+    ni = blk.num_interface_elements
+    assert ni % 4 == 0 or ni == blk.premesh.num_elements
+    assert not touching[ni:].any()
+    assert touching[:ni].sum() == touching.sum()
     # Dirichlet flags = global boundary only
     onb = (np.abs(np.abs(x) - 1.0) < 1e-12).any(axis=1)
     np.testing.assert_array_equal(blk.dirichlet, onb)

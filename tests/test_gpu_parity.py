@@ -309,7 +309,9 @@ def test_operator_apply_matches_oracle(case, dtype):
   interior = 1.0 - bmask
   op = space.operator(dirichlet_mask=bmask, with_mass=True)
   tol = TOL[dtype] * (20 if dtype == torch.float32 else 1)
-  variants = [0, 1] if qt == GLL and q1d == n1d and ndim > 1 else [0]
+  # 0: default specialised kernels (three-/two-mapping, bulk-async staging),
+  # 1: generic runtime-(N, Q) kernel, 2: v1 specialised kernels
+  variants = [0, 1, 2] if qt == GLL and q1d == n1d and ndim > 1 else [0]
   for lam, mu in ((0.0, 1.0), (1.0, 0.0), (1833.3, 0.7)):
     want = oracle.apply(u, lam=lam, mu=mu, interior_mask=interior)
     for variant in variants:
@@ -446,6 +448,40 @@ def test_fused_cg_matches_oracle(case, precond):
                  M=(None if M is None else (lambda r: M(r))))
   assert abs(infog['num_iterations'] - info_want['num_iterations']) <= 1
   assert rel_err(xg.cpu(), x_want) < 1e-6
+
+
+def test_cg_building_blocks_match_fused_solver():
+  """distributed_cg on one rank (no halo) == sfem_cg, bit for bit in count."""
+  from swirl_fem_b200.communication.dist_cg import distributed_cg
+  from swirl_fem_b200.core.operator import JacobiPreconditioner
+  from swirl_fem_b200.linalg.cg import cg
+  refined, mesh, space, oracle, bmask = _build(3, 3, 5, GLL, 5, torch.float64)
+  op = space.operator(dirichlet_mask=bmask, with_mass=True)
+  b = op.apply(torch.ones(mesh.num_nodes, dtype=torch.float64, device='cuda'),
+               lam=1.0, mu=0.0)
+  minv = op.jacobi_minv()
+  x1, i1 = cg(op.bind(0.0, 1.0), b, tol=1e-9, M=JacobiPreconditioner(minv))
+  x2, i2 = distributed_cg(op, None, b, tol=1e-9, minv=minv, check_every=5)
+  assert i1['num_iterations'] == i2['num_iterations']
+  assert rel_err(x2.cpu(), x1.cpu()) < 1e-10
+  x3, i3 = distributed_cg(op, None, b, tol=1e-12, maxiter=4, minv=None)
+  assert i3['num_iterations'] == 4
+
+
+def test_multi_gpu_partitioned_parity():
+  """2 ranks over NCCL vs the unpartitioned solve (needs >= 2 GPUs)."""
+  import os
+  import subprocess
+  import sys
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs at least 2 GPUs')
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+         '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+         '--master-port', '29533', os.path.join(root, 'tools',
+                                                'check_multi_gpu.py')]
+  proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+  assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
 
 
 def test_config1_poisson_32x32_p4_iteration_counts():
