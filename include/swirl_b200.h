@@ -103,6 +103,15 @@ int sfem_halo_pack(int dtype, const void* u, const int32_t* idx, int64_t count,
                    void* buf, sfem_stream_t stream);
 int sfem_halo_unpack_add(int dtype, void* u, const int32_t* idx, int64_t count,
                          const void* buf, sfem_stream_t stream);
+/* Canonical form of the unpack: for each of the `num_dofs` unique interface
+ * dofs, u[dofs[i]] = sum of the contributions src[row_ptr[i] .. row_ptr[i+1])
+ * in the stored (ascending rank) order, where src >= 0 indexes `recv` and
+ * src < 0 stands for this rank's own value.  All ranks evaluate the same
+ * expression, so replicated dofs stay bitwise identical across ranks. */
+int sfem_halo_unpack_canonical(int dtype, void* u, const int32_t* dofs,
+                               const int32_t* row_ptr, const int32_t* src,
+                               int64_t num_dofs, const void* recv,
+                               sfem_stream_t stream);
 
 /* ------------------------------------------------------------------------ */
 /* FE space: geometric factors, q-function evaluation, integration          */

@@ -79,6 +79,9 @@ SIGNATURES = {
                                       _c_ptr, _c_ptr]),
     'sfem_halo_unpack_add': (ctypes.c_int, [ctypes.c_int, _c_ptr, _c_ptr,
                                             _c_i64, _c_ptr, _c_ptr]),
+    'sfem_halo_unpack_canonical': (ctypes.c_int, [ctypes.c_int, _c_ptr, _c_ptr,
+                                                  _c_ptr, _c_ptr, _c_i64,
+                                                  _c_ptr, _c_ptr]),
     'sfem_space_create': (ctypes.c_int, [ctypes.POINTER(SpaceDesc), _c_ptr,
                                          _c_ptr, _c_ptr,
                                          ctypes.POINTER(_c_ptr), _c_ptr]),
@@ -295,6 +298,15 @@ def halo_pack(u, idx, buf):
     _check(lib().sfem_halo_pack(dtype_code(u.dtype), ptr(u), ptr(idx),
                                 idx.numel(), ptr(buf), stream_ptr(u.device)),
            'sfem_halo_pack')
+
+
+def halo_unpack_canonical(u, dofs, row_ptr, src, recv):
+  require_cuda(u, dofs, row_ptr, src, recv)
+  with torch.cuda.device(u.device):
+    _check(lib().sfem_halo_unpack_canonical(
+        dtype_code(u.dtype), ptr(u), ptr(dofs), ptr(row_ptr), ptr(src),
+        dofs.numel(), ptr(recv), stream_ptr(u.device)),
+           'sfem_halo_unpack_canonical')
 
 
 def halo_unpack_add(u, idx, buf):

@@ -116,24 +116,63 @@ class HaloPlan:
       self._dev[key] = (idx, send, recv, splits, offs)
     return self._dev[key]
 
+  def canonical_csr(self):
+    """CSR (dofs, row_ptr, src) of the canonical unpack.
+
+    For every unique interface dof: its contributions in ascending RANK order,
+    `src >= 0` = position in the concatenated receive buffer, `src = -1` = this
+    rank's own value.
+    """
+    if 'csr' not in self._dev:
+      entries = []  # (dof, rank, src)
+      off = 0
+      for q in self.peers:
+        loc = self.local_idx[q].astype(np.int64)
+        entries.append(np.stack([loc, np.full(len(loc), q),
+                                 off + np.arange(len(loc))], axis=1))
+        off += len(loc)
+      allp = (np.concatenate(entries) if entries
+              else np.zeros((0, 3), np.int64))
+      dofs = np.unique(allp[:, 0])
+      own = np.stack([dofs, np.full(len(dofs), self.rank),
+                      np.full(len(dofs), -1)], axis=1)
+      allp = np.concatenate([allp, own])
+      order = np.lexsort((allp[:, 1], allp[:, 0]))  # by dof, then rank
+      allp = allp[order]
+      counts = np.bincount(np.searchsorted(dofs, allp[:, 0]),
+                           minlength=len(dofs))
+      row_ptr = np.concatenate([[0], np.cumsum(counts)])
+      self._dev['csr'] = (dofs.astype(np.int32), row_ptr.astype(np.int32),
+                          allp[:, 2].astype(np.int32))
+    return self._dev['csr']
+
+  def _canonical_device(self, device):
+    key = ('csr', str(device))
+    if key not in self._dev:
+      self._dev[key] = tuple(torch.as_tensor(a).to(device)
+                             for a in self.canonical_csr())
+    return self._dev[key]
+
+  def _unpack_canonical(self, u, recv):
+    dofs, row_ptr, src = self._canonical_device(u.device)
+    _lib.halo_unpack_canonical(u, dofs, row_ptr, src, recv)
+
   def exchange_(self, u: torch.Tensor) -> torch.Tensor:
     """In-place QQ^T on this rank's `(num_local_nodes,)` vector.
 
     One pack kernel for all peers, ONE `all_to_all_single` (NCCL grouped
-    send/recv; the host never blocks), then one unpack-add kernel per peer in
-    ascending peer order (a dof shared with several peers occurs once per
-    peer, so the adds of different peers must not race).
+    send/recv; the host never blocks), one canonical unpack kernel: every
+    holder of a dof sums all contributions in ascending rank order, so the
+    replicated values are bitwise identical on all ranks.
     """
     import torch.distributed as dist  # pylint: disable=g-import-not-at-top
     if not self.peers:
       return u
-    idx, send, recv, splits, offs = self._flat_lists(u.device, u.dtype)
+    idx, send, recv, splits, _ = self._flat_lists(u.device, u.dtype)
     self._pack(u, idx, send)
     dist.all_to_all_single(recv, send, output_split_sizes=splits,
                            input_split_sizes=splits, group=self.group)
-    for q in self.peers:
-      lo, hi = int(offs[q]), int(offs[q + 1])
-      self._unpack_add(u, idx[lo:hi], recv[lo:hi])
+    self._unpack_canonical(u, recv)
     return u
 
   # -- split form, used to overlap the wire time with interior compute -------
@@ -153,10 +192,8 @@ class HaloPlan:
 
   def finish_exchange(self, u: torch.Tensor):
     """Unpack-add of the received values (after `start_exchange` completed)."""
-    idx, _, recv, _, offs = self._flat_lists(u.device, u.dtype)
-    for q in self.peers:
-      lo, hi = int(offs[q]), int(offs[q + 1])
-      self._unpack_add(u, idx[lo:hi], recv[lo:hi])
+    _, _, recv, _, _ = self._flat_lists(u.device, u.dtype)
+    self._unpack_canonical(u, recv)
     return u
 
   def exchange(self, u: torch.Tensor) -> torch.Tensor:

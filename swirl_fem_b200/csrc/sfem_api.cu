@@ -301,7 +301,7 @@ int sfem_op_apply_range(const sfem_op* op, double lambda, double mu,
   SFEM_REQUIRE(elem_begin >= 0 && elem_begin <= elem_end &&
                    elem_end <= d.num_elements,
                "element range out of bounds");
-  SFEM_REQUIRE(elem_begin % 4 == 0,
+  SFEM_REQUIRE(elem_begin % 4 == 0 || elem_begin == elem_end,
                "elem_begin must be a multiple of 4 (16-byte aligned chunks)");
   SFEM_REQUIRE(lambda == 0.0 || op->with_mass,
                "operator was created without mass factors but lambda != 0");

@@ -29,10 +29,20 @@ struct Cfg2DV2 {
   static constexpr int n = N * N;
   static constexpr int epb = EPB;
   static constexpr int threads = ((EPB * N + 31) / 32) * 32;
-  static constexpr int R = pow2_at_least(N);
-  static constexpr int tile = N * R + 4;     // + pad: shifts banks per slot
+  // row pitch / tile size / XOR swizzle from an offline bank-conflict search
+  // over the row-owner and column-owner access patterns
+  static constexpr int R = (sizeof(T) == 8 ? kTile2D64 : kTile2D32)[N][0];
+  static constexpr int tile = (sizeof(T) == 8 ? kTile2D64 : kTile2D32)[N][1];
+  static constexpr bool SWZ =
+      (sizeof(T) == 8 ? kTile2D64 : kTile2D32)[N][2] != 0;
   static constexpr int tiles_per_slot = 3;   // u[2], work
+  // offset (in T) of the factor stage: 16-byte aligned
+  static constexpr int stage_off =
+      ((EPB * tiles_per_slot * tile * (int)sizeof(T) + 15) / 16) * 16 /
+      (int)sizeof(T);
 };
+
+#define SFEM_SW(a, b) (SWZ ? ((a) ^ (b)) : (a))
 
 template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB>
 __global__ void __launch_bounds__((Cfg2DV2<T, N, EPB>::threads), MINB)
@@ -43,6 +53,7 @@ apply2d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
                   int64_t E, double* __restrict__ dot_xy) {
   using C = Cfg2DV2<T, N, EPB>;
   constexpr int n = C::n, epb = C::epb, R = C::R;
+  constexpr bool SWZ = C::SWZ;
   constexpr int ngeom = MASS ? 4 : 3;
   constexpr unsigned gbytes = (unsigned)(ngeom * n * sizeof(T));
   constexpr unsigned cbytes = (unsigned)(n * sizeof(uint32_t));
@@ -55,7 +66,7 @@ apply2d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
 
   // shared layout: [tiles (epb*3)] [factor stage (epb*ngeom*n)] [conn ring 3x]
   T* tiles = reinterpret_cast<T*>(smem_raw);
-  T* sG0 = tiles + epb * C::tiles_per_slot * C::tile;
+  T* sG0 = tiles + C::stage_off;
   uint32_t* sC0 = reinterpret_cast<uint32_t*>(sG0 + epb * ngeom * n);
 
   const int slot = threadIdx.x / N;
@@ -66,7 +77,7 @@ apply2d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
   T* sU0 = tiles + s_ * C::tiles_per_slot * C::tile;
   T* sW = sU0 + 2 * C::tile;
   const T* sG = sG0 + s_ * (ngeom * n);
-  const int ts = t & (R - 1);
+  const int ts = t;
   // swizzled tile index: (i, j) -> i * R + (j ^ i)
   const bool want_dot = !LOCAL && dot_xy != nullptr;
   double dot = 0.0;
@@ -98,7 +109,7 @@ apply2d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     const uint32_t* cn = sC0 + ring * (epb * n) + slot * n + t * N;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      T* d = dst + t * R + (j ^ ts);
+      T* d = dst + t * R + SFEM_SW(j, ts);
       if (act) {
         if (LOCAL) {
           cp_async_elem(d, x + ((e * n + t * N + j) * (int64_t)ncomp + c));
@@ -163,14 +174,14 @@ apply2d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     T row[N], ds[N];
     if (lane_ok) {
 #pragma unroll
-      for (int m = 0; m < N; ++m) row[m] = sU[t * R + (m ^ ts)];
+      for (int m = 0; m < N; ++m) row[m] = sU[t * R + SFEM_SW(m, ts)];
       eo_apply<T, N>(dm.fwd, row, ds);  // d/d(a1) along the row
       T col[N], dr[N];
 #pragma unroll
-      for (int m = 0; m < N; ++m) col[m] = sU[m * R + (ts ^ m)];
+      for (int m = 0; m < N; ++m) col[m] = sU[m * R + SFEM_SW(ts, m)];
       eo_apply<T, N>(dm.fwd, col, dr);  // d/d(a0) along the column
 #pragma unroll
-      for (int m = 0; m < N; ++m) sW[m * R + (ts ^ m)] = dr[m];
+      for (int m = 0; m < N; ++m) sW[m * R + SFEM_SW(ts, m)] = dr[m];
     }
     __syncthreads();
 
@@ -192,11 +203,11 @@ apply2d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       const T* g = sG + t * N;
 #pragma unroll
       for (int j = 0; j < N; ++j) {
-        const T dr = sW[t * R + (j ^ ts)];
+        const T dr = sW[t * R + SFEM_SW(j, ts)];
         const T g00 = active ? g[j] : T(0);
         const T g01 = active ? g[n + j] : T(0);
         const T g11 = active ? g[2 * n + j] : T(0);
-        sW[t * R + (j ^ ts)] = mu * (g00 * dr + g01 * ds[j]);
+        sW[t * R + SFEM_SW(j, ts)] = mu * (g00 * dr + g01 * ds[j]);
         ws[j] = mu * (g01 * dr + g11 * ds[j]);
         if (MASS) row[j] *= lambda * (active ? g[3 * n + j] : T(0));
       }
@@ -214,10 +225,10 @@ apply2d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     if (lane_ok) {
       T col[N], out[N];
 #pragma unroll
-      for (int m = 0; m < N; ++m) col[m] = sW[m * R + (ts ^ m)];
+      for (int m = 0; m < N; ++m) col[m] = sW[m * R + SFEM_SW(ts, m)];
       eo_apply<T, N>(dm.bwd, col, out);
 #pragma unroll
-      for (int m = 0; m < N; ++m) sW[m * R + (ts ^ m)] = out[m];
+      for (int m = 0; m < N; ++m) sW[m * R + SFEM_SW(ts, m)] = out[m];
     }
     __syncthreads();
 
@@ -226,7 +237,7 @@ apply2d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       const uint32_t* cn = sC0 + ring * (epb * n) + slot * n + t * N;
 #pragma unroll
       for (int j = 0; j < N; ++j) {
-        const T v = yrow[j] + sW[t * R + (j ^ ts)];
+        const T v = yrow[j] + sW[t * R + SFEM_SW(j, ts)];
         if (LOCAL) {
           y[(e * n + t * N + j) * (int64_t)ncomp + c] = v;
         } else {
@@ -240,7 +251,7 @@ apply2d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
                 *dst = v;
               else
                 red_add(dst, v);
-              if (want_dot) dot += (double)sU[t * R + (j ^ ts)] * (double)v;
+              if (want_dot) dot += (double)sU[t * R + SFEM_SW(j, ts)] * (double)v;
             }
           }
         }
@@ -262,9 +273,9 @@ int launch2d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
   constexpr int ngeom = MASS ? 4 : 3;
   const int64_t E = op.base.desc.num_elements;
   const int64_t nsteps = (E + EPB - 1) / EPB;
-  const size_t smem = (size_t)EPB * (C::tiles_per_slot * C::tile + ngeom * C::n) *
-                          sizeof(T) +
-                      (size_t)3 * EPB * C::n * sizeof(uint32_t);
+  const size_t smem =
+      ((size_t)C::stage_off + (size_t)EPB * ngeom * C::n) * sizeof(T) +
+      (size_t)3 * EPB * C::n * sizeof(uint32_t);
   auto kernel = apply2d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB>;
   static int per_sm = 0;
   if (per_sm == 0) {
@@ -295,7 +306,7 @@ int launch2d_v2(const sfem_op& op, double lambda, double mu, const void* x,
   constexpr int EPB = e0 < 4 ? 4 : e0;
   using C = Cfg2DV2<T, N, EPB>;
   constexpr long smem =
-      (long)EPB * (C::tiles_per_slot * C::tile + (MASS ? 4 : 3) * C::n) *
+      ((long)C::stage_off + (long)EPB * (MASS ? 4 : 3) * C::n) *
           (long)sizeof(T) +
       3L * EPB * C::n * 4;
   constexpr int by_smem = (int)((220L * 1024) / smem);

@@ -166,6 +166,32 @@ unpack_add_kernel(T* __restrict__ u, const int32_t* __restrict__ idx,
     u[idx[i]] += buf[i];  // idx entries are unique within one message
 }
 
+// Canonical halo sum: u[dof] = sum over ALL holders of the dof (this rank and
+// its peers) in ascending rank order, starting from 0.  Every rank that holds
+// the dof evaluates the same floating-point expression, so the replicated
+// values stay bitwise identical across ranks (a chain of in-place adds would
+// associate differently on every rank for dofs with >= 3 holders).
+// CSR over the unique interface dofs; src >= 0: position in `recv`, src < 0:
+// this rank's own value.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+unpack_canonical_kernel(T* __restrict__ u, const int32_t* __restrict__ dofs,
+                        const int32_t* __restrict__ row_ptr,
+                        const int32_t* __restrict__ src, int64_t num_dofs,
+                        const T* __restrict__ recv) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < num_dofs;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t d = dofs[i];
+    const T own = u[d];
+    T acc = T(0);
+    for (int32_t j = row_ptr[i]; j < row_ptr[i + 1]; ++j) {
+      const int32_t s = src[j];
+      acc += s < 0 ? own : recv[s];
+    }
+    u[d] = acc;
+  }
+}
+
 // ---- connectivity packing -------------------------------------------------------
 __global__ void count_kernel(const int32_t* __restrict__ elements, int64_t total,
                              int32_t* __restrict__ counts) {
@@ -443,6 +469,26 @@ int sfem_halo_pack(int dtype, const void* u, const int32_t* idx, int64_t count,
   else
     pack_kernel<float><<<blocks_for(count), kThreads, 0, stream>>>(
         (const float*)u, idx, count, (float*)buf);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_halo_unpack_canonical(int dtype, void* u, const int32_t* dofs,
+                               const int32_t* row_ptr, const int32_t* src,
+                               int64_t num_dofs, const void* recv,
+                               sfem_stream_t stream_) {
+  using namespace sfem;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (num_dofs == 0) return SFEM_OK;
+  SFEM_REQUIRE(u && dofs && row_ptr && src, "null argument");
+  if (dtype == SFEM_F64)
+    unpack_canonical_kernel<double><<<blocks_for(num_dofs), kThreads, 0,
+                                      stream>>>(
+        (double*)u, dofs, row_ptr, src, num_dofs, (const double*)recv);
+  else
+    unpack_canonical_kernel<float><<<blocks_for(num_dofs), kThreads, 0,
+                                     stream>>>(
+        (float*)u, dofs, row_ptr, src, num_dofs, (const float*)recv);
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }

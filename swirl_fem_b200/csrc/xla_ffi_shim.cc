@@ -1,0 +1,104 @@
+// XLA typed-FFI shim over the C ABI of libswirl_b200 (include/swirl_b200.h), so
+// that the entry points can be bound as `jax.ffi` custom calls
+// (jax.ffi.register_ffi_target(name, jax.ffi.pycapsule(fn), platform="CUDA")).
+//
+// HEADER-GATED: jax / jaxlib (and therefore xla/ffi/api/ffi.h) are NOT
+// installed in the build image and there is no network, so this file compiles
+// to an empty translation unit here and is NOT part of libswirl_b200.so.  It
+// is the binding a maintainer of the reference builds next to jaxlib:
+//   g++ -shared -fPIC -I$(python -c "import jaxlib; print(jaxlib.__path__[0])")/include \
+//       xla_ffi_shim.cc -L../lib -lswirl_b200 -o libswirl_b200_xla.so
+// The tested binding of the same C symbols is ctypes + torch (swirl_fem_b200/_lib.py).
+#if __has_include("xla/ffi/api/ffi.h")
+
+#include <cuda_runtime_api.h>
+
+#include "../../include/swirl_b200.h"
+#include "xla/ffi/api/ffi.h"
+
+namespace ffi = xla::ffi;
+
+static int DtypeOf(ffi::DataType t) {
+  return t == ffi::DataType::F64 ? SFEM_F64 : SFEM_F32;
+}
+
+static ffi::Error Status(int rc) {
+  if (rc == SFEM_OK) return ffi::Error::Success();
+  return ffi::Error(rc == SFEM_ERR_UNSUPPORTED ? ffi::ErrorCode::kUnimplemented
+                                               : ffi::ErrorCode::kInternal,
+                    sfem_last_error());
+}
+
+// gather_scatter.gather (swirl_fem/core/gather_scatter.py:121-127)
+static ffi::Error GatherImpl(cudaStream_t stream, ffi::AnyBuffer u,
+                             ffi::Buffer<ffi::DataType::S32> indices,
+                             ffi::Result<ffi::AnyBuffer> out, double fill) {
+  return Status(sfem_gather(DtypeOf(u.element_type()), u.untyped_data(),
+                            indices.typed_data(), indices.element_count(), fill,
+                            1, 0, out->untyped_data(), (sfem_stream_t)stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(sfem_xla_gather, GatherImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::Buffer<ffi::DataType::S32>>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<double>("fill_value"));
+
+// gather_scatter.scatter (gather_scatter.py:130-133)
+static ffi::Error ScatterImpl(cudaStream_t stream, ffi::AnyBuffer u_local,
+                              ffi::Buffer<ffi::DataType::S32> indices,
+                              ffi::Result<ffi::AnyBuffer> out) {
+  return Status(sfem_scatter_add(
+      DtypeOf(u_local.element_type()), u_local.untyped_data(),
+      indices.typed_data(), indices.element_count(), out->element_count(), 1, 0,
+      out->untyped_data(), (sfem_stream_t)stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(sfem_xla_scatter_add, ScatterImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::Buffer<ffi::DataType::S32>>()
+                                  .Ret<ffi::AnyBuffer>());
+
+// A(u) = mask . scatter(local_covector(a, (gather(u), v)))
+// (swirl_fem/examples/poisson.py:141-146); `handle` = address of the sfem_op
+// created once outside jit.
+static ffi::Error OpApplyImpl(cudaStream_t stream, ffi::AnyBuffer x,
+                              ffi::Result<ffi::AnyBuffer> y, int64_t handle,
+                              double lam, double mu) {
+  const auto dims = x.dimensions();
+  const int ncomp = dims.size() == 2 ? (int)dims[1] : 1;
+  return Status(sfem_op_apply(reinterpret_cast<const sfem_op*>(handle), lam, mu,
+                              x.untyped_data(), y->untyped_data(), ncomp,
+                              nullptr, (sfem_stream_t)stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(sfem_xla_op_apply, OpApplyImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<int64_t>("handle")
+                                  .Attr<double>("lam")
+                                  .Attr<double>("mu"));
+
+// FiniteElementSpace.local_covector (swirl_fem/core/fespace.py:405-471)
+static ffi::Error OpApplyLocalImpl(cudaStream_t stream, ffi::AnyBuffer u_local,
+                                   ffi::Result<ffi::AnyBuffer> y_local,
+                                   int64_t handle, double lam, double mu) {
+  const auto dims = u_local.dimensions();
+  const int ncomp = dims.size() == 3 ? (int)dims[2] : 1;
+  return Status(sfem_op_apply_local(
+      reinterpret_cast<const sfem_op*>(handle), lam, mu, u_local.untyped_data(),
+      y_local->untyped_data(), ncomp, (sfem_stream_t)stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(sfem_xla_op_apply_local, OpApplyLocalImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<int64_t>("handle")
+                                  .Attr<double>("lam")
+                                  .Attr<double>("mu"));
+
+#endif  // __has_include("xla/ffi/api/ffi.h")

@@ -36,6 +36,15 @@ class CpuHaloPlan(HaloPlan):
   def _unpack_add(self, u, idx, buf):
     u[idx.long()] += buf
 
+  def _unpack_canonical(self, u, recv):
+    dofs, row_ptr, src = self.canonical_csr()
+    own = u.clone()
+    for i, d in enumerate(dofs):
+      acc = torch.zeros((), dtype=u.dtype)
+      for j in range(row_ptr[i], row_ptr[i + 1]):
+        acc = acc + (own[d] if src[j] < 0 else recv[src[j]])
+      u[d] = acc
+
 
 def _free_port():
   with socket.socket() as s:
@@ -107,6 +116,20 @@ def _worker_block(rank, world, port, ndim, ne, n1d):
     # multiplicity of every local node over ranks
     mult = plan.exchange(torch.ones_like(u)).numpy()
     np.testing.assert_allclose(out, mult * f, rtol=1e-13)
+    # canonical unpack: replicated dofs are BITWISE identical on all holders
+    # (values chosen so that the sum depends on the association order)
+    rng = np.random.default_rng(7)
+    noisy = torch.tensor(f * (1.0 + 1e-3 * rng.standard_normal(len(f))) *
+                         (1.0 + 0.37 * rank), dtype=torch.float64)
+    summed = plan.exchange(noisy).numpy()
+    mine = dict(zip(blk.interface_global.tolist(),
+                    summed[blk.interface_local].tolist()))
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    for other in everyone:
+      for gid, val in other.items():
+        if gid in mine:
+          assert mine[gid] == val, (gid, mine[gid], val)
     # owned weights count every global dof exactly once
     total = torch.tensor([float(plan.owned.sum())], dtype=torch.float64)
     dist.all_reduce(total)

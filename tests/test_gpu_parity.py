@@ -450,6 +450,88 @@ def test_fused_cg_matches_oracle(case, precond):
   assert rel_err(xg.cpu(), x_want) < 1e-6
 
 
+def test_config3_velocity_helmholtz_solve_periodic():
+  """BASELINE config 3 (hot-path part): the velocity Helmholtz solve of
+  `stokes_one_step` -- H_ = (beta_k/dt) B + mu A on a vector GLL field with
+  M = velocity.exchange (swirl_fem/navier_stokes/navier_stokes.py:286-307,
+  431-438) on the 9x9 y-periodic order-7 mesh of navier_stokes_test.py:39-77.
+  """
+  from swirl_fem_b200.common.premesh_commons import unit_cube_mesh
+  from swirl_fem_b200.core.interpolation import Nodes1D, Quadrature1D
+  from swirl_fem_b200.core.mesh_refiner import refine_premesh
+  from swirl_fem_b200.core.operator import FusedOperator
+  from swirl_fem_b200.linalg.cg import cg
+  n1d = 8
+  pm = unit_cube_mesh(9, ndim=2, a=0., b=2 * np.pi, periodic_dims=(1,))
+  refined = refine_premesh(pm, Nodes1D.create(n1d, GLL))
+  host = refined.finalize_host()
+  mesh = refined.finalize()
+  quad = Quadrature1D.create_from_nodes_1d(Nodes1D.create(n1d, GLL))
+  bmask = host['physical_masks']['boundary']
+  op = FusedOperator(mesh, quad, dirichlet_mask=bmask, with_mass=True)
+  oracle = dense.FESpace(refined.node_coords, refined.elements, n1d,
+                         helpers.TNAME[GLL], n1d, helpers.TNAME[GLL])
+  interior = 1.0 - bmask
+  gi, ui = host['exchange_gather_indices'], host['exchange_unique_indices']
+  lam, mu = (11.0 / 6.0) / 1e-3, 1.0  # beta_3 / dt, navier_stokes_test.py:281
+  massdiag = oracle.mass_diag()
+  # device operators with the reference's structure: B is the lumped mass
+  md = dev(massdiag)
+  imask = dev(interior)
+
+  def H_dev(u):  # (G, 2) AoS
+    return lam * imask[:, None] * md[:, None] * u + mu * op.apply(u, 0.0, 1.0)
+
+  def exch_dev(u):
+    return torch.stack([mesh.exchange(u[:, k].contiguous())
+                        for k in range(2)], -1)
+
+  def H_or(u):
+    return lam * (interior * massdiag)[:, None] * u + mu * np.stack(
+        [oracle.apply(u[:, k], 0.0, 1.0, interior) for k in range(2)], -1)
+
+  def exch_or(u):
+    return np.stack([dense.exchange(u[:, k], gi, ui) for k in range(2)], -1)
+
+  x = refined.node_coords
+  f = np.stack([np.sin(x[:, 0]) * np.cos(x[:, 1]),
+                -np.cos(x[:, 0]) * np.sin(x[:, 1])], -1) * interior[:, None]
+  u_or, info_or = dense.cg(H_or, f, tol=1e-12, M=exch_or,
+                           dot_fn=lambda a, b: float(np.vdot(a, b)))
+  u, info = cg(H_dev, dev(f), tol=1e-12, M=exch_dev)
+  assert abs(info['num_iterations'] - info_or['num_iterations']) <= 1
+  assert rel_err(u.cpu(), u_or) < 1e-9
+  # exchange of a vector field matches the oracle's QQ^T
+  assert rel_err(exch_dev(dev(f)).cpu(), exch_or(f)) < 1e-14
+
+
+def test_config2_helmholtz_shuffled_quads_order8():
+  """BASELINE config 2 at test size: Helmholtz (lumped-mass form is covered
+  above; here the consistent form lam*M + mu*K) on an 'unstructured' quad mesh
+  (random element order and per-element vertex re-orientation), order 8."""
+  from swirl_fem_b200.core.operator import JacobiPreconditioner
+  from swirl_fem_b200.linalg.cg import cg
+  refined, mesh, space, oracle, bmask = _build(2, 6, 9, GLL, 9, torch.float64,
+                                               seed=21)
+  interior = 1.0 - bmask
+  lam, mu = (11.0 / 6.0) / 1e-3, 1.0
+  op = space.operator(dirichlet_mask=bmask, with_mass=True)
+  rng = np.random.default_rng(5)
+  u = rng.standard_normal(mesh.num_nodes)
+  want = oracle.apply(u, lam=lam, mu=mu, interior_mask=interior)
+  assert rel_err(op.apply(dev(u), lam=lam, mu=mu).cpu(), want) < 1e-12
+  b = oracle.apply(np.ones(mesh.num_nodes), 1.0, 0.0, interior)
+  x_or, info_or = dense.cg(
+      lambda v: oracle.apply(v, lam, mu, interior), b, tol=1e-10)
+  xs, info = cg(op.bind(lam, mu), dev(b), tol=1e-10)
+  assert abs(info['num_iterations'] - info_or['num_iterations']) <= 1
+  assert rel_err(xs.cpu(), x_or) < 1e-8
+  # Jacobi with the Helmholtz diagonal converges at least as fast
+  M = JacobiPreconditioner(op.jacobi_minv(lam, mu))
+  xj, infoj = cg(op.bind(lam, mu), dev(b), tol=1e-10, M=M)
+  assert rel_err(xj.cpu(), x_or) < 1e-7
+
+
 def test_cg_building_blocks_match_fused_solver():
   """distributed_cg on one rank (no halo) == sfem_cg, bit for bit in count."""
   from swirl_fem_b200.communication.dist_cg import distributed_cg

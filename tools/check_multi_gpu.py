@@ -70,7 +70,7 @@ def main():
     y2 = torch.empty_like(y)
     dot2 = torch.zeros((), dtype=torch.float64, device=dev)
     op.apply_partitioned(u, y2, halo, blk.num_interface_elements, lam=0.3,
-                         mu=1.0, dot_out=dot2)
+                         mu=1.0, dot_out=dot2, overlap=True)
     torch.cuda.synchronize()
     assert float((y2 - y).abs().max()) <= 1e-13 * float(y.abs().max()), (
         'overlapped apply differs from apply + exchange')
