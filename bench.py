@@ -325,11 +325,23 @@ def run_ours(args):
   abytes = algorithmic_bytes(mesh.num_nodes, num_local_nodes, args.dim, esz)
   peak, peak_src = measured_peak_gbs()
   achieved = abytes / (apply_ms * 1e-3) / 1e9
+  # DRAM traffic of the kernel from a recorded `ncu --set full` capture of this
+  # exact workload (profiles/traffic.json); null for other workloads
+  traffic, traffic_src = None, None
+  try:
+    with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+      rec = json.load(f).get(
+          f'{args.dim}d_p{args.order}_{args.dtype}_ne{args.ne}_n{world}')
+    if rec:
+      traffic, traffic_src = rec['traffic_bytes_per_launch'], rec['source']
+  except (OSError, ValueError, KeyError):
+    pass
   roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak,
-              'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+              'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+              'traffic_source': traffic_src,
               'peak_source': peak_src,
-              'kernel': 'apply3d_kernel (memset of shared-dof prefix + fused '
-                        'gather/operator/scatter)',
+              'kernel': 'apply3d_v2_kernel (memset of the shared-dof prefix + '
+                        'fused gather/operator/scatter)',
               'algorithmic_bytes_per_launch': abytes,
               'kernel_ms': apply_ms,
               'frac_of_nominal_8TBs': achieved / 8000.0}

@@ -517,68 +517,77 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
   return SFEM_OK;
 }
 
+// Launch configuration for a given elements-per-CTA count: whether the factors
+// are staged (bulk async copies) and how many CTAs an SM should hold (shared
+// memory footprint and a register estimate).
+template <typename T, int N, bool MASS, int EPB>
+struct AutoCfg3D {
+  using C0 = Cfg3DV2<T, N, EPB, 1, 0>;
+  static constexpr long stage_bytes =
+      ((long)C0::stage_off(EPB) + (long)EPB * (MASS ? 7 : 6) * C0::n) *
+      (long)sizeof(T);
+  static constexpr bool staged =
+      stage_bytes <= 200 * 1024 &&
+      (((MASS ? 7 : 6) * C0::n * sizeof(T)) % 16) == 0;
+  static constexpr int KCH = staged ? 0 : 2;
+  static constexpr long smem_bytes =
+      staged ? stage_bytes : (long)C0::stage_off(EPB) * (long)sizeof(T);
+  static constexpr int by_smem =
+      (int)((220L * 1024) / (smem_bytes > 0 ? smem_bytes : 1));
+  static constexpr int est_regs_raw = 40 + (sizeof(T) == 8 ? 18 : 9) * N;
+  static constexpr int est_regs = est_regs_raw > 255 ? 255 : est_regs_raw;
+  static constexpr int by_regs = 65536 / (C0::threads * est_regs);
+  static constexpr int m0 = by_smem < by_regs ? by_smem : by_regs;
+  static constexpr int MINB = m0 < 1 ? 1 : (m0 > 8 ? 8 : m0);
+};
+
+constexpr int clamp_int(int v, int lo, int hi) {
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+
 template <typename T, int N, bool MASS, bool LOCAL>
 int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
                 void* y, int ncomp, double* dot_xy, cudaStream_t stream) {
-  constexpr int E0 = default_epb<N>();
+  // Default: small CTAs (>= 64 threads fp64, >= 128 fp32); see AutoCfg3D.
+  constexpr int P = N * N;
+  constexpr int target = sizeof(T) == 8 ? 64 : 128;
+  constexpr int EPB = clamp_int((target + P - 1) / P, 1, 16);
+  using A = AutoCfg3D<T, N, MASS, EPB>;
 #ifdef SFEM_EXPERIMENTS
-  // tuning variants, compiled only for the headline configuration
-  if constexpr (N == 8 && !MASS && !LOCAL) {
+  // tuning variants (relative to the default), fp64 Laplacian, N = 5..9 only
+  if constexpr (sizeof(T) == 8 && N >= 5 && N <= 9 && !MASS && !LOCAL) {
+    constexpr int Ep = clamp_int(EPB + 1, 1, 16), Em = clamp_int(EPB - 1, 1, 16);
+    constexpr int E2 = clamp_int(EPB * 2, 1, 16);
+    using Ap = AutoCfg3D<T, N, MASS, Ep>;
+    using Am = AutoCfg3D<T, N, MASS, Em>;
+    using A2 = AutoCfg3D<T, N, MASS, E2>;
     switch (op.variant) {
-      case 3:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 1, 5, 0>(
+      case 3:  // one more element per CTA
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, Ep, Ap::MINB, Ap::KCH>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
-      case 4:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 1, 4, 0>(
+      case 4:  // one fewer
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, Em, Am::MINB, Am::KCH>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
-      case 5:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 2, 2, 0>(
+      case 5:  // twice as many
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, E2, A2::MINB, A2::KCH>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
-      case 6:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 1, 8, 2>(
+      case 6:  // one more resident CTA (tighter register cap)
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB,
+                               clamp_int(A::MINB + 1, 1, 8), A::KCH>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
-      case 7:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 1, 3, 0>(
+      case 7:  // one fewer resident CTA (looser register cap)
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB,
+                               clamp_int(A::MINB - 1, 1, 8), A::KCH>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
-      case 8:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 2, 3, 0>(
-            op, lambda, mu, x, y, ncomp, dot_xy, stream);
-      case 9:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 1, 6, 0>(
-            op, lambda, mu, x, y, ncomp, dot_xy, stream);
-      case 10:
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, 4, 1, 0>(
+      case 8:  // no staging: factors streamed from L2 in batches of 2 slabs
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, 2>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
       default:
         break;
     }
   }
 #endif
-  (void)E0;
-  // Default configuration: small CTAs (>= 64 threads fp64, >= 128 fp32), the
-  // geometric factors staged through shared memory by bulk async copies
-  // whenever the CTA's tiles + stage fit; the number of resident CTAs follows
-  // from the shared-memory footprint and a register estimate.
-  constexpr int P = N * N;
-  constexpr int target = sizeof(T) == 8 ? 64 : 128;
-  constexpr int epb0 = (target + P - 1) / P;
-  constexpr int EPB = epb0 < 1 ? 1 : (epb0 > 16 ? 16 : epb0);
-  using C0 = Cfg3DV2<T, N, EPB, 1, 0>;
-  constexpr long stage_bytes =
-      ((long)C0::stage_off(EPB) + (long)EPB * (MASS ? 7 : 6) * C0::n) *
-      (long)sizeof(T);
-  constexpr bool staged =
-      stage_bytes <= 200 * 1024 && (((MASS ? 7 : 6) * C0::n * sizeof(T)) % 16) == 0;
-  constexpr int KCH = staged ? 0 : 2;
-  constexpr long smem_bytes =
-      staged ? stage_bytes : (long)C0::stage_off(EPB) * (long)sizeof(T);
-  constexpr int by_smem = (int)((220L * 1024) / (smem_bytes > 0 ? smem_bytes : 1));
-  constexpr int est_regs_raw = 40 + (sizeof(T) == 8 ? 18 : 9) * N;
-  constexpr int est_regs = est_regs_raw > 255 ? 255 : est_regs_raw;
-  constexpr int by_regs = 65536 / (C0::threads * est_regs);
-  constexpr int m0 = by_smem < by_regs ? by_smem : by_regs;
-  constexpr int MINB = m0 < 1 ? 1 : (m0 > 8 ? 8 : m0);
-  return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, MINB, KCH>(
+  return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH>(
       op, lambda, mu, x, y, ncomp, dot_xy, stream);
 }
 

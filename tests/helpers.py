@@ -39,11 +39,30 @@ def shuffled(premesh: Premesh, seed: int) -> Premesh:
                         periodic_links=premesh.periodic_links)
 
 
-def deformed_premesh(ndim, ne, n1d, seed=None, periodic_dims=(), curved=True):
+def rotated_quads(premesh: Premesh, seed: int) -> Premesh:
+  """Random element order + per-element 90-degree rotations of the vertex
+  listing.  Unlike `shuffled`, every element keeps a POSITIVE Jacobian
+  determinant (the reference integrates with the signed determinant,
+  fespace.py:346, 402, so reflected elements make the operator indefinite)."""
+  assert premesh.ndim == 2
+  rng = np.random.default_rng(seed)
+  elements = np.array(premesh.elements)[rng.permutation(premesh.num_elements)]
+  out = [np.rot90(el.reshape(2, 2), k=int(rng.integers(4))).reshape(-1)
+         for el in elements]
+  return Premesh.create(node_coords=premesh.node_coords,
+                        elements=np.array(out, dtype=np.int32),
+                        physical_groups=premesh.physical_groups,
+                        periodic_links=premesh.periodic_links)
+
+
+def deformed_premesh(ndim, ne, n1d, seed=None, periodic_dims=(), curved=True,
+                     rotate_seed=None):
   """Refined GLL premesh on [-1,1]^ndim with deformed (curved) elements."""
   pm = unit_cube_mesh(ne, ndim=ndim, a=-1., b=1., periodic_dims=periodic_dims)
   if seed is not None:
     pm = shuffled(pm, seed)
+  if rotate_seed is not None:
+    pm = rotated_quads(pm, rotate_seed)
   refined = refine_premesh(pm, Nodes1D.create(n1d, GLL))
   if curved and not periodic_dims:
     refined = refined.replace(node_coords=deform(refined.node_coords))

@@ -277,10 +277,12 @@ def test_integrate_generic_quad():
 # ----------------------------------------------------------------------------
 
 
-def _build(ndim, ne, n1d, quad_type, q1d, dtype, seed=None, with_bc=True):
+def _build(ndim, ne, n1d, quad_type, q1d, dtype, seed=None, with_bc=True,
+           rotate_seed=None):
   from swirl_fem_b200.core.fespace import FiniteElementSpace
   from swirl_fem_b200.core.interpolation import Quadrature1D
-  refined = helpers.deformed_premesh(ndim, ne, n1d, seed=seed)
+  refined = helpers.deformed_premesh(ndim, ne, n1d, seed=seed,
+                                     rotate_seed=rotate_seed)
   mesh = refined.finalize(dtype=dtype)
   space = FiniteElementSpace.create(mesh, Quadrature1D.create(q1d, quad_type))
   oracle = dense.FESpace(refined.node_coords, refined.elements, n1d,
@@ -508,11 +510,15 @@ def test_config3_velocity_helmholtz_solve_periodic():
 def test_config2_helmholtz_shuffled_quads_order8():
   """BASELINE config 2 at test size: Helmholtz (lumped-mass form is covered
   above; here the consistent form lam*M + mu*K) on an 'unstructured' quad mesh
-  (random element order and per-element vertex re-orientation), order 8."""
+  (random element order and per-element rotation of the vertex listing; the
+  rotations keep det J > 0 -- the reference integrates with the SIGNED
+  determinant, so reflected elements would make the operator indefinite),
+  order 8."""
   from swirl_fem_b200.core.operator import JacobiPreconditioner
   from swirl_fem_b200.linalg.cg import cg
   refined, mesh, space, oracle, bmask = _build(2, 6, 9, GLL, 9, torch.float64,
-                                               seed=21)
+                                               rotate_seed=21)
+  assert (oracle.jacdets > 0).all()
   interior = 1.0 - bmask
   lam, mu = (11.0 / 6.0) / 1e-3, 1.0
   op = space.operator(dirichlet_mask=bmask, with_mass=True)
