@@ -251,7 +251,10 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
   // one bulk async copy (TMA 1-D) per element, completion on an mbarrier
   constexpr bool STAGE = KCH == 0;
   constexpr unsigned gbytes = (unsigned)(ngeom * n * sizeof(T));
-  static_assert(!STAGE || gbytes % 16 == 0, "bulk copy needs 16 B multiples");
+  // a CTA step's chunk (EPB elements) must start 16-byte aligned; the last
+  // step rounds its size up to 16 bytes (the allocator pads the buffer)
+  static_assert(!STAGE || (EPB * gbytes) % 16 == 0,
+                "bulk copy needs 16 B aligned CTA chunks");
   // (the CTA's `epb` elements are consecutive, so it is ONE copy per CTA step)
   __shared__ __align__(8) uint64_t gbar;
   T* sG0 = smem + C::stage_off(epb);
@@ -261,7 +264,7 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     // elected thread: refill the stage with the factors of CTA step `blk_id`
     const int64_t first = blk_id * epb;
     const int64_t count = (E - first) < epb ? (E - first) : epb;
-    const unsigned bytes = (unsigned)count * gbytes;
+    const unsigned bytes = ((unsigned)count * gbytes + 15u) & ~15u;
     mbar_expect_tx(&gbar, bytes);
     bulk_copy_g2s(sG0, gf + first * (int64_t)(ngeom * n), bytes, &gbar);
   };
@@ -528,13 +531,15 @@ struct AutoCfg3D {
       (long)sizeof(T);
   static constexpr bool staged =
       stage_bytes <= 200 * 1024 &&
-      (((MASS ? 7 : 6) * C0::n * sizeof(T)) % 16) == 0;
+      ((EPB * (MASS ? 7 : 6) * C0::n * sizeof(T)) % 16) == 0;
   static constexpr int KCH = staged ? 0 : 2;
   static constexpr long smem_bytes =
       staged ? stage_bytes : (long)C0::stage_off(EPB) * (long)sizeof(T);
   static constexpr int by_smem =
       (int)((220L * 1024) / (smem_bytes > 0 ? smem_bytes : 1));
-  static constexpr int est_regs_raw = 40 + (sizeof(T) == 8 ? 18 : 9) * N;
+  // register estimate fitted to ptxas output (fp64: 114 @ N=5 ... 180 @ N=9)
+  static constexpr int est_regs_raw =
+      sizeof(T) == 8 ? 26 + 17 * N : 40 + 9 * N;
   static constexpr int est_regs = est_regs_raw > 255 ? 255 : est_regs_raw;
   static constexpr int by_regs = 65536 / (C0::threads * est_regs);
   static constexpr int m0 = by_smem < by_regs ? by_smem : by_regs;
@@ -551,7 +556,15 @@ int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
   // Default: small CTAs (>= 64 threads fp64, >= 128 fp32); see AutoCfg3D.
   constexpr int P = N * N;
   constexpr int target = sizeof(T) == 8 ? 64 : 128;
-  constexpr int EPB = clamp_int((target + P - 1) / P, 1, 16);
+  constexpr int epb_t = clamp_int((target + P - 1) / P, 1, 16);
+  // an element's factors need not be a multiple of 16 bytes (odd N in fp32,
+  // or with the mass factor): a CTA step then takes the next element count
+  // whose chunk is (the bulk copy needs 16-byte aligned chunks)
+  constexpr long gb = (long)(MASS ? 7 : 6) * N * N * N * (long)sizeof(T);
+  constexpr int EPB = (epb_t * gb) % 16 == 0         ? epb_t
+                      : ((epb_t + 1) * gb) % 16 == 0 ? epb_t + 1
+                      : ((epb_t + 2) * gb) % 16 == 0 ? epb_t + 2
+                                                     : epb_t + 3;
   using A = AutoCfg3D<T, N, MASS, EPB>;
 #ifdef SFEM_EXPERIMENTS
   // tuning variants (relative to the default), fp64 Laplacian, N = 5..9 only
