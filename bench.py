@@ -260,13 +260,22 @@ def run_ours(args):
   quad = Quadrature1D.create_from_nodes_1d(grid1d)
   # Only the fused operator is needed: no invjacs / jacdets / quad_coords.
   op = FusedOperator(mesh, quad, dirichlet_mask=blk.dirichlet, with_mass=False)
-  halo = None
+  halo, halo_path = None, None
   if world > 1:
     gathered = [None] * world
     dist.all_gather_object(gathered, np.sort(blk.interface_global))
     halo = part.halo_plan_from_interfaces(
         rank, blk.interface_local, blk.interface_global, gathered,
         mesh.num_nodes)
+    # shared-dof exchange over peer memory (NVLink stores issued from inside
+    # the apply kernel); SFEM_HALO=nccl keeps the pack / all_to_all / unpack
+    # path for comparison
+    if os.environ.get('SFEM_HALO', 'p2p') == 'p2p':
+      halo_path = ('peer memory (in-kernel NVLink push)'
+                   if halo.enable_p2p(dtype, device) else
+                   'nccl all_to_all (peer mapping failed)')
+    else:
+      halo_path = 'nccl all_to_all'
   torch.cuda.synchronize()
   t_setup = time.perf_counter() - t_setup
 
@@ -440,6 +449,7 @@ def run_ours(args):
         'config': {
             'workload': config_name(args),
             'partition': 'x'.join(str(g) for g in blk.grid),
+            'halo_exchange': halo_path,
             'local_dofs_rank0': mesh.num_nodes,
             'elements_rank0': mesh.num_elements,
             'l2_policy': 'inputs larger than L2 (geometric factors '

@@ -218,6 +218,85 @@ int sfem_op_diag(const sfem_op* op, double lambda, double mu, void* diag,
 int sfem_op_set_variant(sfem_op* op, int32_t variant);
 
 /* ------------------------------------------------------------------------ */
+/* Peer-memory halo exchange (partitioned QQ^T over NVLink P2P stores)       */
+/* ------------------------------------------------------------------------ */
+
+/* The reference's partitioned exchange is ONE dense lax.psum over all shared
+ * dofs (swirl_fem/core/gather_scatter.py:246-248).  Here every rank owns a
+ * peer-mapped region (CUDA IPC) holding its flag words and two receive
+ * buffers (epoch parity); a rank writes its shared dofs directly into its
+ * peers' buffers with NVLink stores and raises a flag, the receiver waits for
+ * its peers' flags and sums all holders' values in ascending rank order.
+ *
+ * sfem_ipc_*: device memory that other processes on the node can map.
+ *   alloc: cudaMalloc + zero + export (handle: 64 bytes, host);
+ *   open:  map a region exported by another process (peer access enabled). */
+#define SFEM_IPC_HANDLE_BYTES 64
+int sfem_ipc_alloc(int64_t bytes, void** dev_ptr, void* handle);
+int sfem_ipc_open(const void* handle, void** dev_ptr);
+int sfem_ipc_close(void* dev_ptr);
+int sfem_ipc_free(void* dev_ptr);
+
+typedef struct {
+  int32_t dtype;
+  int32_t rank, world;
+  int32_t num_peers;
+  /* send side */
+  int64_t num_send;              /* entries, all peers concatenated          */
+  const int32_t* send_idx;       /* device (num_send): local dof             */
+  const uint64_t* send_dst;      /* device (num_send): address of the slot in
+                                    the peer's parity-0 receive buffer       */
+  uint64_t parity_stride_bytes;  /* parity-1 buffers = parity-0 + this (the
+                                    same on every rank)                      */
+  const uint64_t* peer_flag_addr;/* HOST (num_peers): address of this rank's
+                                    parity-0 flag word on each peer; the
+                                    parity-1 word is `world` words further   */
+  /* receive side */
+  const int32_t* peer_ranks;     /* HOST (num_peers), ascending              */
+  const uint64_t* flags;         /* device (2 * world): this rank's flag words
+                                    [parity][source rank]                    */
+  const void* recv;              /* device: parity-0 receive buffer          */
+  /* canonical sum (see sfem_halo_unpack_canonical) */
+  int64_t num_dofs;
+  const int32_t* dofs;
+  const int32_t* row_ptr;
+  const int32_t* src;
+} sfem_halo_desc;
+
+typedef struct sfem_halo sfem_halo;
+
+/* All device arrays of the descriptor must outlive the handle. */
+int sfem_halo_create(const sfem_halo_desc* desc, sfem_halo** halo);
+void sfem_halo_destroy(sfem_halo* halo);
+
+/* Starts a new epoch: u's shared dofs -> the peers' receive buffers, then
+ * this rank's flag is raised on every peer.  Never waits. */
+int sfem_halo_push(sfem_halo* halo, const void* u, sfem_stream_t stream);
+
+/* Waits (on the device) for the current epoch's flags of all peers, then
+ * u[dof] = sum over all holders in ascending rank order.  Every rank must
+ * run the same sequence of push / wait_unpack calls. */
+int sfem_halo_wait_unpack(sfem_halo* halo, void* u, sfem_stream_t stream);
+
+/* First half of y = QQ^T (mask . scatter(local_op(gather(x)))) on an
+ * element-partitioned mesh whose first `num_interface_elements` elements are
+ * the ones touching other ranks' blocks: ONE apply launch that pushes the
+ * shared dofs of y to the peers as soon as all interface elements are done,
+ * while the interior elements are still being computed (3-D collocated
+ * kernels; other kernel families run the apply, then sfem_halo_push).  The
+ * caller completes the exchange with sfem_halo_wait_unpack(halo, y) -- work
+ * that does not read y's shared dofs may be enqueued in between.  ncomp = 1.
+ * dot_xy as in sfem_op_apply (the local, pre-exchange x . y: element-wise
+ * partial sums need no ownership weights). */
+int sfem_op_apply_halo(const sfem_op* op, sfem_halo* halo, double lambda,
+                       double mu, const void* x, void* y,
+                       int64_t num_interface_elements, void* dot_xy,
+                       sfem_stream_t stream);
+
+/* 1 if the last wait of this handle timed out (peer never raised its flag). */
+int sfem_halo_timed_out(const sfem_halo* halo, sfem_stream_t stream);
+
+/* ------------------------------------------------------------------------ */
 /* CG (swirl_fem/linalg/cg.py:30-97)                                         */
 /* ------------------------------------------------------------------------ */
 

@@ -51,6 +51,19 @@ class CgParams(ctypes.Structure):
   ]
 
 
+class HaloDesc(ctypes.Structure):
+  """`sfem_halo_desc`."""
+  _fields_ = [
+      ('dtype', _c_i32), ('rank', _c_i32), ('world', _c_i32),
+      ('num_peers', _c_i32),
+      ('num_send', _c_i64), ('send_idx', _c_ptr), ('send_dst', _c_ptr),
+      ('parity_stride_bytes', ctypes.c_uint64), ('peer_flag_addr', _c_ptr),
+      ('peer_ranks', _c_ptr), ('flags', _c_ptr), ('recv', _c_ptr),
+      ('num_dofs', _c_i64), ('dofs', _c_ptr), ('row_ptr', _c_ptr),
+      ('src', _c_ptr),
+  ]
+
+
 class CgInfo(ctypes.Structure):
   """`sfem_cg_info`."""
   _fields_ = [('residual', _c_f64), ('num_iterations', _c_i64)]
@@ -82,6 +95,19 @@ SIGNATURES = {
     'sfem_halo_unpack_canonical': (ctypes.c_int, [ctypes.c_int, _c_ptr, _c_ptr,
                                                   _c_ptr, _c_ptr, _c_i64,
                                                   _c_ptr, _c_ptr]),
+    'sfem_ipc_alloc': (ctypes.c_int, [_c_i64, ctypes.POINTER(_c_ptr), _c_ptr]),
+    'sfem_ipc_open': (ctypes.c_int, [_c_ptr, ctypes.POINTER(_c_ptr)]),
+    'sfem_ipc_close': (ctypes.c_int, [_c_ptr]),
+    'sfem_ipc_free': (ctypes.c_int, [_c_ptr]),
+    'sfem_halo_create': (ctypes.c_int, [ctypes.POINTER(HaloDesc),
+                                        ctypes.POINTER(_c_ptr)]),
+    'sfem_halo_destroy': (None, [_c_ptr]),
+    'sfem_halo_push': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr]),
+    'sfem_halo_wait_unpack': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr]),
+    'sfem_halo_timed_out': (ctypes.c_int, [_c_ptr, _c_ptr]),
+    'sfem_op_apply_halo': (ctypes.c_int, [_c_ptr, _c_ptr, _c_f64, _c_f64,
+                                          _c_ptr, _c_ptr, _c_i64, _c_ptr,
+                                          _c_ptr]),
     'sfem_space_create': (ctypes.c_int, [ctypes.POINTER(SpaceDesc), _c_ptr,
                                          _c_ptr, _c_ptr,
                                          ctypes.POINTER(_c_ptr), _c_ptr]),

@@ -15,6 +15,7 @@ QQ^T; parity is checked against the unpartitioned oracle.
 
 from __future__ import annotations
 
+import ctypes
 import dataclasses
 
 import numpy as np
@@ -23,6 +24,55 @@ import torch
 from swirl_fem_b200 import _lib
 
 SENTINEL = -1
+
+
+def _round_up(v: int, m: int) -> int:
+  return -(-int(v) // m) * m
+
+
+def p2p_region_layout(world: int, max_recv_entries: int, esz: int):
+  """Layout of a rank's peer-mapped region (the same on every rank).
+
+  `[flag words: 2 parities x world x 8 B | receive buffer parity 0 | parity 1]`
+  Returns `(flag_bytes, parity_stride_bytes, total_bytes)`.
+  """
+  flag_bytes = _round_up(2 * world * 8, 256)
+  stride = _round_up(max(max_recv_entries, 1) * esz, 256)
+  return flag_bytes, stride, flag_bytes + 2 * stride
+
+
+def p2p_tables(rank: int, peers, counts, all_splits, bases, esz: int):
+  """Destination tables of the peer-memory push (pure host arithmetic).
+
+  Args:
+    rank: this rank.
+    peers: ascending peer ranks.
+    counts: peer -> number of dofs shared with it.
+    all_splits: `all_splits[q][r]` = number of dofs ranks q and r share (every
+      rank's `splits`); rank q's receive buffer is the concatenation of its
+      peers' segments in ascending rank order.
+    bases: peer -> address of the peer's region as mapped in this process.
+    esz: bytes per value.
+  Returns:
+    `(send_dst uint64 (num_send,), peer_flag_addr uint64 (num_peers,))`:
+    the address of every send entry's slot in its peer's parity-0 receive
+    buffer, and of this rank's parity-0 flag word on every peer.
+  """
+  world = len(all_splits)
+  flag_bytes, _, _ = p2p_region_layout(world, 0, esz)
+  dst, flag_addr = [], []
+  for q in peers:
+    n = int(counts[q])
+    if int(all_splits[q][rank]) != n:
+      raise ValueError(
+          f'ranks {rank} and {q} disagree on the number of shared dofs '
+          f'({n} vs {all_splits[q][rank]})')
+    seg = int(np.sum(np.asarray(all_splits[q][:rank], dtype=np.int64)))
+    start = int(bases[q]) + flag_bytes + seg * esz
+    dst.append(np.uint64(start) + np.arange(n, dtype=np.uint64) * np.uint64(esz))
+    flag_addr.append(int(bases[q]) + rank * 8)
+  send_dst = (np.concatenate(dst) if dst else np.zeros(0, np.uint64))
+  return send_dst.astype(np.uint64), np.asarray(flag_addr, dtype=np.uint64)
 
 
 def default_rank() -> int:
@@ -105,8 +155,7 @@ class HaloPlan:
     """Concatenated (all peers) index list, buffers and split sizes."""
     key = ('flat', str(device), dtype)
     if key not in self._dev:
-      splits = [len(self.local_idx[q]) if q in self.local_idx else 0
-                for q in range(self.world)]
+      splits = self.splits()
       cat = (np.concatenate([self.local_idx[q] for q in self.peers])
              if self.peers else np.zeros(0, np.int32))
       idx = torch.as_tensor(cat.astype(np.int32)).to(device)
@@ -157,6 +206,153 @@ class HaloPlan:
     dofs, row_ptr, src = self._canonical_device(u.device)
     _lib.halo_unpack_canonical(u, dofs, row_ptr, src, recv)
 
+  # -- peer-memory path (NVLink P2P stores, no NCCL on the data path) -------
+  def splits(self):
+    return [len(self.local_idx[q]) if q in self.local_idx else 0
+            for q in range(self.world)]
+
+  def _p2p_attach(self, dtype, device, region_ptr, bases, all_splits):
+    """Builds the `sfem_halo` handle once every region address is known."""
+    esz = torch.empty((), dtype=dtype).element_size()
+    flag_bytes, stride, _ = p2p_region_layout(
+        self.world, max(int(np.sum(sp)) for sp in all_splits), esz)
+    send_dst, flag_addr = p2p_tables(
+        self.rank, self.peers, {q: len(v) for q, v in self.local_idx.items()},
+        all_splits, bases, esz)
+    idx, _, _, _, _ = self._flat_lists(device, dtype)
+    dofs, row_ptr, src = self._canonical_device(device)
+    send_dst_t = torch.as_tensor(send_dst.view(np.int64)).to(device)
+    peer_ranks = np.asarray(self.peers, dtype=np.int32)
+    desc = _lib.HaloDesc(
+        dtype=_lib.dtype_code(dtype), rank=self.rank, world=self.world,
+        num_peers=len(self.peers), num_send=idx.numel(),
+        send_idx=idx.data_ptr(), send_dst=send_dst_t.data_ptr(),
+        parity_stride_bytes=stride,
+        peer_flag_addr=flag_addr.ctypes.data,
+        peer_ranks=peer_ranks.ctypes.data,
+        flags=region_ptr, recv=region_ptr + flag_bytes,
+        num_dofs=dofs.numel(), dofs=dofs.data_ptr(),
+        row_ptr=row_ptr.data_ptr(), src=src.data_ptr())
+    handle = ctypes.c_void_p()
+    with torch.cuda.device(device):
+      _lib._check(_lib.lib().sfem_halo_create(ctypes.byref(desc),
+                                              ctypes.byref(handle)),
+                  'sfem_halo_create')
+    self._p2p = {'handle': handle, 'dtype': dtype, 'device': device,
+                 'region': region_ptr, 'keep': (send_dst_t, idx, dofs, row_ptr,
+                                                src)}
+
+  def enable_p2p(self, dtype, device, group=None) -> bool:
+    """Switches the exchange of `dtype` vectors to peer-memory stores.
+
+    Collective: every rank of `group` must call it.  Each rank exports one
+    region (CUDA IPC), maps its peers' regions and builds the destination
+    tables.  Returns False (and keeps the NCCL path) if peer mapping fails on
+    any rank.
+    """
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    lib = _lib.lib()
+    esz = torch.empty((), dtype=dtype).element_size()
+    all_splits = [None] * self.world
+    dist.all_gather_object(all_splits, self.splits(), group=group)
+    _, _, total = p2p_region_layout(
+        self.world, max(int(np.sum(sp)) for sp in all_splits), esz)
+    ok, region, handle_bytes = True, ctypes.c_void_p(), bytes(64)
+    buf = ctypes.create_string_buffer(64)
+    with torch.cuda.device(device):
+      if lib.sfem_ipc_alloc(total, ctypes.byref(region), buf) != 0:
+        ok = False
+      else:
+        handle_bytes = bytes(buf.raw)
+    handles = [None] * self.world
+    dist.all_gather_object(handles, (ok, handle_bytes), group=group)
+    ok = all(h[0] for h in handles)
+    bases = {}
+    if ok:
+      with torch.cuda.device(device):
+        for q in self.peers:
+          mapped = ctypes.c_void_p()
+          if lib.sfem_ipc_open(handles[q][1], ctypes.byref(mapped)) != 0:
+            ok = False
+            break
+          bases[q] = mapped.value
+    flags = [None] * self.world
+    dist.all_gather_object(flags, ok, group=group)
+    if not all(flags):
+      return False
+    if self.peers:
+      self._p2p_attach(dtype, device, region.value, bases, all_splits)
+      self._p2p['mapped'] = bases
+    torch.cuda.synchronize(device)
+    dist.barrier(group=group)
+    return True
+
+  @staticmethod
+  def enable_p2p_local(plans, dtype, device):
+    """All ranks in ONE process on one device (tests): regions are plain
+    device allocations, peers' addresses are used directly."""
+    lib = _lib.lib()
+    esz = torch.empty((), dtype=dtype).element_size()
+    all_splits = [pl.splits() for pl in plans]
+    _, _, total = p2p_region_layout(
+        len(plans), max(int(np.sum(sp)) for sp in all_splits), esz)
+    regions = []
+    with torch.cuda.device(device):
+      for _ in plans:
+        region = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(64)
+        _lib._check(lib.sfem_ipc_alloc(total, ctypes.byref(region), buf),
+                    'sfem_ipc_alloc')
+        regions.append(region.value)
+    for pl in plans:
+      if pl.peers:
+        pl._p2p_attach(dtype, device, regions[pl.rank],
+                       {q: regions[q] for q in pl.peers}, all_splits)
+
+  def disable_p2p(self):
+    """Releases the peer-memory handle, the mapped peer regions and this
+    rank's region (collective in effect: peers must have stopped pushing)."""
+    p = getattr(self, '_p2p', None)
+    if p is None:
+      return
+    lib = _lib.lib()
+    with torch.cuda.device(p['device']):
+      torch.cuda.synchronize(p['device'])
+      lib.sfem_halo_destroy(p['handle'])
+      for addr in p.get('mapped', {}).values():
+        lib.sfem_ipc_close(addr)
+      if 'mapped' in p:
+        import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+        dist.barrier(group=self.group)
+      lib.sfem_ipc_free(p['region'])
+    self._p2p = None
+
+  def p2p_handle(self, u: torch.Tensor):
+    p = getattr(self, '_p2p', None)
+    if p is None or p['dtype'] != u.dtype or u.dim() != 1:
+      return None
+    return p['handle']
+
+  def p2p_push(self, u: torch.Tensor):
+    with torch.cuda.device(u.device):
+      _lib._check(_lib.lib().sfem_halo_push(
+          self.p2p_handle(u), _lib.ptr(u), _lib.stream_ptr(u.device)),
+                  'sfem_halo_push')
+
+  def p2p_wait_unpack(self, u: torch.Tensor):
+    with torch.cuda.device(u.device):
+      _lib._check(_lib.lib().sfem_halo_wait_unpack(
+          self.p2p_handle(u), _lib.ptr(u), _lib.stream_ptr(u.device)),
+                  'sfem_halo_wait_unpack')
+
+  def p2p_timed_out(self, device) -> bool:
+    p = getattr(self, '_p2p', None)
+    if p is None:
+      return False
+    with torch.cuda.device(device):
+      return bool(_lib.lib().sfem_halo_timed_out(p['handle'],
+                                                 _lib.stream_ptr(device)))
+
   def exchange_(self, u: torch.Tensor) -> torch.Tensor:
     """In-place QQ^T on this rank's `(num_local_nodes,)` vector.
 
@@ -167,6 +363,11 @@ class HaloPlan:
     """
     import torch.distributed as dist  # pylint: disable=g-import-not-at-top
     if not self.peers:
+      return u
+    if self.p2p_handle(u) is not None:
+      # peer-memory path: NVLink stores into the peers' buffers + flags
+      self.p2p_push(u)
+      self.p2p_wait_unpack(u)
       return u
     idx, send, recv, splits, _ = self._flat_lists(u.device, u.dtype)
     self._pack(u, idx, send)

@@ -128,8 +128,13 @@ class FusedOperator:
   def apply_partitioned(self, x: torch.Tensor, out: torch.Tensor, halo,
                         num_interface_elements: int, lam: float = 0.0,
                         mu: float = 1.0, dot_out: torch.Tensor | None = None,
-                        overlap: bool = False):
+                        overlap: bool = False, wait: bool = True):
     """Partitioned apply: local apply + shared-dof (halo) exchange.
+
+    With a peer-memory halo (`HaloPlan.enable_p2p`) this is the fused path:
+    `sfem_op_apply_halo` (one launch; the push to the peers happens inside the
+    kernel as soon as the interface elements are done) followed by the
+    wait + canonical sum (`wait=False` leaves that to the caller).
 
     `overlap=True`: elements `[0, num_interface_elements)` are the ones
     touching another rank's block (`communication.partition` stores them
@@ -145,6 +150,22 @@ class FusedOperator:
     ni = int(num_interface_elements)
     if halo is None or not halo.peers:
       return self.apply(x, lam=lam, mu=mu, out=out, dot_out=dot_out)
+    hp = halo.p2p_handle(x) if hasattr(halo, 'p2p_handle') else None
+    if hp is not None and not overlap:
+      # ONE launch: interface elements first, shared dofs pushed to the peers
+      # over NVLink from inside the kernel while the interior elements are
+      # computed; then the wait + canonical sum (sfem_halo.cu)
+      _lib.require_cuda(x, out)
+      assert x.is_contiguous() and out.is_contiguous()
+      assert x.dtype == self.dtype and out.dtype == self.dtype
+      with torch.cuda.device(x.device):
+        _lib._check(_lib.lib().sfem_op_apply_halo(
+            self.handle, hp, float(lam), float(mu), _lib.ptr(x),
+            _lib.ptr(out), ni, _lib.ptr(dot_out), _lib.stream_ptr(x.device)),
+                    'sfem_op_apply_halo')
+      if wait:
+        halo.p2p_wait_unpack(out)
+      return out
     if not overlap:
       self.apply(x, lam=lam, mu=mu, out=out, dot_out=dot_out)
       halo.exchange_(out)

@@ -208,14 +208,25 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc,
       : "memory");
 }
 
-template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH>
+// HALO: the CTA steps [0, hd.n_if_blocks) hold the elements that touch another
+// rank's block.  A CTA that has finished its share of them signals a global
+// counter; once every CTA has, the shared dofs of y are final on this rank and
+// the CTAs push them (slice by slice, between two element steps) straight into
+// the peers' receive buffers over NVLink while the interior elements are still
+// being computed -- the exchange costs no extra launch and no wire time on
+// the critical path.  Nothing ever spins: a CTA that exits before the counter
+// completes leaves its slices to the CTAs that are still running (the last
+// signaller always is).
+template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH,
+          bool HALO = false>
 __global__ void __launch_bounds__((Cfg3DV2<T, N, EPB, MINB, KCH>::threads),
                                   MINB)
 apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
                   const uint32_t* __restrict__ conn,
                   const T* __restrict__ gf, T lambda, T mu,
                   const T* __restrict__ x, T* __restrict__ y, int ncomp,
-                  int64_t E, double* __restrict__ dot_xy) {
+                  int64_t E, double* __restrict__ dot_xy,
+                  const __grid_constant__ HaloDev hd) {
   using C = Cfg3DV2<T, N, EPB, MINB, KCH>;
   constexpr int P = C::P, n = C::n, epb = C::epb;
   constexpr int S0 = C::S0, R = C::R;
@@ -300,6 +311,11 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
   }
   cp_async_commit();
 
+  // HALO state (block-uniform): 0 interface steps pending, 1 signalled and
+  // waiting for the other CTAs, 2 pushed
+  __shared__ unsigned s_halo[2];
+  int hstate = 0;
+
   int buf = 0;
   for (; blk < nblocks; blk += gridDim.x, buf ^= 1) {
     T* sU = sU0 + buf * C::tile;
@@ -327,9 +343,27 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       }
     }
 
+    if (HALO && threadIdx.x == 0)
+      s_halo[0] = hstate == 1 && ld_acquire_gpu(&hd.counters[0]) >= gridDim.x;
+
     // ---- u tile of this element has landed (cp.async issued one element ago)
     cp_async_wait_all();
     __syncthreads();
+
+    if (HALO) {
+      if (hstate == 0 && blk >= hd.n_if_blocks) {
+        // every thread fenced its y updates at the end of the last interface
+        // step and has passed the barrier above
+        if (threadIdx.x == 0) {
+          __threadfence();
+          atomicAdd(&hd.counters[0], 1u);
+        }
+        hstate = 1;
+      } else if (hstate == 1 && s_halo[0]) {
+        halo_push_slices<T>(hd, y, &s_halo[1]);
+        hstate = 2;
+      }
+    }
 
     // ---- phase 2 (mappings B, C): a1- and a2-derivatives
     if (lane_ok) {
@@ -479,15 +513,34 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     active = active_n;
 #pragma unroll
     for (int k = 0; k < N; ++k) rc[k] = nrc[k];
+    if (HALO && hstate == 0 && blk_n >= hd.n_if_blocks) __threadfence();
   }
   cp_async_wait_all();
+  if (HALO) {
+    if (hstate == 0) {  // all steps of this CTA were interface steps
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&hd.counters[0], 1u);
+      }
+      hstate = 1;
+    }
+    if (hstate == 1) {
+      __syncthreads();
+      if (threadIdx.x == 0)
+        s_halo[0] = ld_acquire_gpu(&hd.counters[0]) >= gridDim.x;
+      __syncthreads();
+      if (s_halo[0]) halo_push_slices<T>(hd, y, &s_halo[1]);
+    }
+  }
   if (want_dot) {
     dot = block_sum(dot, red);
     if (threadIdx.x == 0) atomicAdd(dot_xy, dot);
   }
 }
 
-template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH>
+template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH,
+          bool HALO = false>
 int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
                     void* y, int ncomp, double* dot_xy, cudaStream_t stream) {
   using C = Cfg3DV2<T, N, EPB, MINB, KCH>;
@@ -497,7 +550,7 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
       ((size_t)C::stage_off(C::epb) +
        (KCH == 0 ? (size_t)C::epb * (MASS ? 7 : 6) * C::n : 0)) *
       sizeof(T);
-  auto kernel = apply3d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB, KCH>;
+  auto kernel = apply3d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB, KCH, HALO>;
   static int per_sm = 0;
   if (per_sm == 0) {
     if (smem > 48 * 1024)
@@ -513,9 +566,18 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
   DOps<T, N> dm;
   fill_even_odd<T, N>(op.base.h_BD, false, &dm.fwd);
   fill_even_odd<T, N>(op.base.h_BD, true, &dm.bwd);
+  HaloDev hd{};
+  if (HALO) {
+    if (op.fuse == nullptr || ncomp != 1) {
+      set_error("fused halo push needs a halo and ncomp == 1");
+      return SFEM_ERR_INVALID;
+    }
+    hd = *op.fuse;  // n_if_blocks arrives as an ELEMENT count
+    hd.n_if_blocks = (hd.n_if_blocks + C::epb - 1) / C::epb;
+  }
   kernel<<<grid, C::threads, smem, stream>>>(
       dm, op.conn, (const T*)op.geom, (T)lambda, (T)mu, (const T*)x, (T*)y,
-      ncomp, E, dot_xy);
+      ncomp, E, dot_xy, hd);
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }
@@ -550,21 +612,26 @@ constexpr int clamp_int(int v, int lo, int hi) {
   return v < lo ? lo : (v > hi ? hi : v);
 }
 
-template <typename T, int N, bool MASS, bool LOCAL>
-int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
-                void* y, int ncomp, double* dot_xy, cudaStream_t stream) {
-  // Default: small CTAs (>= 64 threads fp64, >= 128 fp32); see AutoCfg3D.
+// Elements per CTA step of the default configuration: small CTAs (>= 64
+// threads fp64, >= 128 fp32).  An element's factors need not be a multiple of
+// 16 bytes (odd N in fp32, or with the mass factor): a CTA step then takes the
+// next element count whose chunk is (bulk copies need 16-byte aligned chunks).
+template <typename T, int N, bool MASS>
+constexpr int default_epb3d() {
   constexpr int P = N * N;
   constexpr int target = sizeof(T) == 8 ? 64 : 128;
   constexpr int epb_t = clamp_int((target + P - 1) / P, 1, 16);
-  // an element's factors need not be a multiple of 16 bytes (odd N in fp32,
-  // or with the mass factor): a CTA step then takes the next element count
-  // whose chunk is (the bulk copy needs 16-byte aligned chunks)
   constexpr long gb = (long)(MASS ? 7 : 6) * N * N * N * (long)sizeof(T);
-  constexpr int EPB = (epb_t * gb) % 16 == 0         ? epb_t
-                      : ((epb_t + 1) * gb) % 16 == 0 ? epb_t + 1
-                      : ((epb_t + 2) * gb) % 16 == 0 ? epb_t + 2
-                                                     : epb_t + 3;
+  return (epb_t * gb) % 16 == 0         ? epb_t
+         : ((epb_t + 1) * gb) % 16 == 0 ? epb_t + 1
+         : ((epb_t + 2) * gb) % 16 == 0 ? epb_t + 2
+                                        : epb_t + 3;
+}
+
+template <typename T, int N, bool MASS, bool LOCAL>
+int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
+                void* y, int ncomp, double* dot_xy, cudaStream_t stream) {
+  constexpr int EPB = default_epb3d<T, N, MASS>();
   using A = AutoCfg3D<T, N, MASS, EPB>;
 #ifdef SFEM_EXPERIMENTS
   // tuning variants (relative to the default), fp64 Laplacian, N = 5..9 only
@@ -602,6 +669,16 @@ int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
 #endif
   return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH>(
       op, lambda, mu, x, y, ncomp, dot_xy, stream);
+}
+
+// Default configuration of launch3d_v2 with the halo push fused in.
+template <typename T, int N, bool MASS>
+int launch3d_v2_halo(const sfem_op& op, double lambda, double mu, const void* x,
+                     void* y, double* dot_xy, cudaStream_t stream) {
+  constexpr int EPB = default_epb3d<T, N, MASS>();
+  using A = AutoCfg3D<T, N, MASS, EPB>;
+  return launch3d_v2_cfg<T, N, MASS, false, EPB, A::MINB, A::KCH, true>(
+      op, lambda, mu, x, y, 1, dot_xy, stream);
 }
 
 }  // namespace

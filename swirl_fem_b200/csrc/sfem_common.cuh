@@ -100,6 +100,78 @@ __device__ __forceinline__ T ld_stream(const T* p) {
   return __ldcs(p);
 }
 
+// ---- peer-memory halo push (shared by the fused apply and sfem_halo_push) -------
+// Everything the device side of a push needs; filled per call by the host
+// (`sfem_halo` handle, sfem_halo.cu) and passed to kernels by value.
+struct HaloDev {
+  const int32_t* send_idx;    // (num_send) local dof of every send entry
+  const uint64_t* send_dst;   // (num_send) address of the entry's slot in the
+                              // peer's receive buffer of parity 0
+  int64_t num_send;
+  uint64_t parity_off;        // byte offset of this epoch's receive buffers
+  const uint64_t* peer_flag;  // (num_peers) address of THIS rank's flag word
+                              // (parity 0) in each peer's flag array
+  uint64_t flag_parity_off;   // byte offset of this epoch's flag words
+  int num_peers;
+  unsigned num_slices;        // ceil(num_send / slice)
+  unsigned slice;             // send entries per work item
+  unsigned* counters;         // [0] CTAs past the interface elements,
+                              // [1] next slice, [2] slices done, [3] unpack
+                              // CTAs done, [4] wait timed out
+  uint64_t epoch;
+  int64_t n_if_blocks;        // CTA steps that cover the interface elements
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Cooperative push of the shared dofs into the peers' receive buffers (P2P
+// stores over NVLink).  Called by ALL threads of a CTA (block-uniform); CTAs
+// draw slices of the send list from a global counter until none is left.  The
+// CTA that completes the last slice raises this rank's flag on every peer
+// (release at system scope, after every writer fenced its stores).
+// `y` values were produced by other CTAs (RED / stores): read them from L2.
+template <typename T>
+__device__ __forceinline__ void halo_push_slices(const HaloDev& h, const T* y,
+                                                 unsigned* s_slice) {
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) *s_slice = atomicAdd(&h.counters[1], 1u);
+    __syncthreads();
+    const unsigned s = *s_slice;
+    if (s >= h.num_slices) break;
+    const int64_t b = (int64_t)s * h.slice;
+    const int64_t e = b + h.slice < h.num_send ? b + h.slice : h.num_send;
+    for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+      const T v = __ldcg(y + __ldg(h.send_idx + i));
+      *reinterpret_cast<T*>(__ldg(h.send_dst + i) + h.parity_off) = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned done = atomicAdd(&h.counters[2], 1u) + 1u;
+      if (done == h.num_slices) {
+        __threadfence_system();
+        for (int k = 0; k < h.num_peers; ++k)
+          st_release_sys(reinterpret_cast<uint64_t*>(h.peer_flag[k] +
+                                                     h.flag_parity_off),
+                         h.epoch);
+      }
+    }
+  }
+}
+
 // symmetric index of (i,k), i<=k, in the packed d(d+1)/2 layout
 __host__ __device__ constexpr int sym_index(int dim, int i, int k) {
   return dim == 1 ? 0
@@ -152,4 +224,7 @@ struct sfem_op {
   uint32_t* conn;   // (E, N^d) packed connectivity
   int64_t n_zero;   // y[0 .. n_zero) must be zeroed before an apply
   int variant;      // 0 auto, 1 generic
+  // set on a shallow copy by sfem_op_apply_halo: fuse the halo push into the
+  // apply kernel (interface elements first)
+  const sfem::HaloDev* fuse = nullptr;
 };

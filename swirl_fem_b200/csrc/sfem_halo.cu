@@ -1,0 +1,310 @@
+// Peer-memory halo exchange: the partitioned QQ^T of
+// swirl_fem/core/gather_scatter.py:221-261 (one dense lax.psum under pmap)
+// restated as direct NVLink stores into the peers' receive buffers.
+//
+//   push    (fused into the 3-D apply kernel, or the standalone kernel below):
+//           recv_peer[slot] = y[dof] for every (peer, shared dof) pair, then
+//           flag_peer[parity][me] = epoch          (st.release.sys)
+//   wait    flag_me[parity][peer] >= epoch for all peers (ld.acquire.sys),
+//   unpack  y[dof] = sum over all holders in ascending rank order (canonical:
+//           every rank evaluates the same expression -> replicated dofs stay
+//           bitwise identical).
+//
+// Two receive buffers / flag sets alternate with the epoch parity: a peer can
+// only start epoch e+2 after it has seen this rank's flag of epoch e+1, which
+// this rank raises after its unpack of epoch e (stream order), so a buffer is
+// never overwritten while it is still being read.
+
+#include <cstring>
+
+#include "sfem_common.cuh"
+
+struct sfem_halo {
+  sfem_halo_desc desc;
+  uint64_t* d_peer_flag = nullptr;  // device copy of desc.peer_flag_addr
+  int32_t* d_peer_ranks = nullptr;
+  unsigned* d_counters = nullptr;   // 8 words, see HaloDev::counters
+  uint64_t epoch = 0;
+  unsigned slice = 256;
+};
+
+namespace sfem {
+
+template <typename T>
+int launch_apply3d_halo(const sfem_op& op, double lambda, double mu,
+                        const void* x, void* y, double* dot_xy,
+                        cudaStream_t stream);
+int op_apply_internal(const sfem_op* op, double lambda, double mu,
+                      const void* x, void* y, int ncomp, double* dot_xy,
+                      cudaStream_t stream);
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+halo_push_kernel(const T* __restrict__ y, const __grid_constant__ HaloDev hd) {
+  __shared__ unsigned s_slice;
+  halo_push_slices<T>(hd, y, &s_slice);
+}
+
+// Spins (bounded: ~4 s of globaltimer) until every peer raised its flag of
+// this epoch, then runs the canonical sum.  The last CTA to finish resets the
+// handle's counters for the next epoch.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+halo_wait_unpack_kernel(T* __restrict__ u, const int32_t* __restrict__ dofs,
+                        const int32_t* __restrict__ row_ptr,
+                        const int32_t* __restrict__ src, int64_t num_dofs,
+                        const T* recv, const uint64_t* flags,
+                        const int32_t* __restrict__ peer_ranks, int num_peers,
+                        uint64_t epoch, unsigned* counters) {
+  for (int k = threadIdx.x; k < num_peers; k += blockDim.x) {
+    const uint64_t* f = flags + peer_ranks[k];
+    uint64_t t0 = 0;
+    unsigned spins = 0;
+    while (ld_acquire_sys(f) < epoch) {
+      if ((++spins & 1023u) == 0) {
+        uint64_t now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 4000000000ull) {
+          atomicExch(&counters[4], 1u);
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < num_dofs;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t d = dofs[i];
+    const T own = u[d];
+    T acc = T(0);
+    for (int32_t j = row_ptr[i]; j < row_ptr[i + 1]; ++j) {
+      const int32_t s = src[j];
+      acc += s < 0 ? own : __ldcg(recv + s);
+    }
+    u[d] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(&counters[3], 1u) + 1u;
+    if (done == gridDim.x) {
+      counters[0] = 0;
+      counters[1] = 0;
+      counters[2] = 0;
+      counters[3] = 0;
+      __threadfence();
+    }
+  }
+}
+
+HaloDev begin_epoch(sfem_halo* h, int64_t num_interface_elements) {
+  h->epoch += 1;
+  const unsigned parity = (unsigned)(h->epoch & 1u);
+  HaloDev hd{};
+  hd.send_idx = h->desc.send_idx;
+  hd.send_dst = h->desc.send_dst;
+  hd.num_send = h->desc.num_send;
+  hd.parity_off = parity ? h->desc.parity_stride_bytes : 0;
+  hd.peer_flag = h->d_peer_flag;
+  hd.flag_parity_off = parity ? (uint64_t)h->desc.world * 8u : 0u;
+  hd.num_peers = h->desc.num_peers;
+  hd.slice = h->slice;
+  hd.num_slices = (unsigned)((h->desc.num_send + h->slice - 1) / h->slice);
+  hd.counters = h->d_counters;
+  hd.epoch = h->epoch;
+  hd.n_if_blocks = num_interface_elements;
+  return hd;
+}
+
+int push_standalone(sfem_halo* h, const HaloDev& hd, const void* u,
+                    cudaStream_t stream) {
+  int blocks = (int)hd.num_slices;
+  const int cap = num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (h->desc.dtype == SFEM_F64)
+    halo_push_kernel<double><<<blocks, kThreads, 0, stream>>>((const double*)u,
+                                                              hd);
+  else
+    halo_push_kernel<float><<<blocks, kThreads, 0, stream>>>((const float*)u,
+                                                             hd);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+}  // namespace
+}  // namespace sfem
+
+extern "C" {
+
+int sfem_ipc_alloc(int64_t bytes, void** dev_ptr, void* handle) {
+  using namespace sfem;
+  SFEM_REQUIRE(bytes > 0 && dev_ptr && handle, "bad argument");
+  void* p = nullptr;
+  SFEM_CUDA_CHECK(cudaMalloc(&p, (size_t)bytes));
+  SFEM_CUDA_CHECK(cudaMemset(p, 0, (size_t)bytes));
+  SFEM_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == SFEM_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    set_error(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    return SFEM_ERR_CUDA;
+  }
+  memcpy(handle, &h, sizeof(h));
+  *dev_ptr = p;
+  return SFEM_OK;
+}
+
+int sfem_ipc_open(const void* handle, void** dev_ptr) {
+  using namespace sfem;
+  SFEM_REQUIRE(handle && dev_ptr, "null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  SFEM_CUDA_CHECK(
+      cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return SFEM_OK;
+}
+
+int sfem_ipc_close(void* dev_ptr) {
+  using namespace sfem;
+  if (dev_ptr) SFEM_CUDA_CHECK(cudaIpcCloseMemHandle(dev_ptr));
+  return SFEM_OK;
+}
+
+int sfem_ipc_free(void* dev_ptr) {
+  using namespace sfem;
+  if (dev_ptr) SFEM_CUDA_CHECK(cudaFree(dev_ptr));
+  return SFEM_OK;
+}
+
+int sfem_halo_create(const sfem_halo_desc* desc, sfem_halo** halo) {
+  using namespace sfem;
+  SFEM_REQUIRE(desc && halo, "null argument");
+  SFEM_REQUIRE(desc->dtype == SFEM_F32 || desc->dtype == SFEM_F64, "bad dtype");
+  SFEM_REQUIRE(desc->num_peers >= 1 && desc->num_peers <= kThreads,
+               "num_peers out of range");
+  SFEM_REQUIRE(desc->world >= 2 && desc->rank >= 0 && desc->rank < desc->world,
+               "bad rank / world");
+  SFEM_REQUIRE(desc->num_send > 0 && desc->send_idx && desc->send_dst &&
+                   desc->peer_flag_addr && desc->peer_ranks && desc->flags &&
+                   desc->recv,
+               "null send / receive arrays");
+  SFEM_REQUIRE(desc->num_dofs > 0 && desc->dofs && desc->row_ptr && desc->src,
+               "null canonical-sum arrays");
+  auto* h = new sfem_halo();
+  h->desc = *desc;
+  const size_t np = (size_t)desc->num_peers;
+  cudaError_t e = cudaMalloc(&h->d_peer_flag, np * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_peer_ranks, np * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_counters, 8 * sizeof(unsigned));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(h->d_peer_flag, desc->peer_flag_addr, np * sizeof(uint64_t),
+                   cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(h->d_peer_ranks, desc->peer_ranks, np * sizeof(int32_t),
+                   cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned));
+  if (e != cudaSuccess) {
+    set_error(std::string("sfem_halo_create: ") + cudaGetErrorString(e));
+    sfem_halo_destroy(h);
+    return SFEM_ERR_CUDA;
+  }
+  h->desc.peer_flag_addr = nullptr;  // host arrays are not retained
+  h->desc.peer_ranks = nullptr;
+  *halo = h;
+  return SFEM_OK;
+}
+
+void sfem_halo_destroy(sfem_halo* halo) {
+  if (!halo) return;
+  cudaFree(halo->d_peer_flag);
+  cudaFree(halo->d_peer_ranks);
+  cudaFree(halo->d_counters);
+  delete halo;
+}
+
+int sfem_halo_push(sfem_halo* halo, const void* u, sfem_stream_t stream) {
+  using namespace sfem;
+  SFEM_REQUIRE(halo && u, "null argument");
+  const HaloDev hd = begin_epoch(halo, 0);
+  return push_standalone(halo, hd, u, (cudaStream_t)stream);
+}
+
+int sfem_halo_wait_unpack(sfem_halo* halo, void* u, sfem_stream_t stream_) {
+  using namespace sfem;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SFEM_REQUIRE(halo && u, "null argument");
+  SFEM_REQUIRE(halo->epoch > 0, "wait_unpack before the first push");
+  const sfem_halo_desc& d = halo->desc;
+  const unsigned parity = (unsigned)(halo->epoch & 1u);
+  const uint64_t* flags = d.flags + (parity ? d.world : 0);
+  const char* recv = (const char*)d.recv + (parity ? d.parity_stride_bytes : 0);
+  int64_t b = (d.num_dofs + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)num_sms() * 4;
+  if (b > cap) b = cap;
+  if (d.dtype == SFEM_F64)
+    halo_wait_unpack_kernel<double><<<(int)b, kThreads, 0, stream>>>(
+        (double*)u, d.dofs, d.row_ptr, d.src, d.num_dofs, (const double*)recv,
+        flags, halo->d_peer_ranks, d.num_peers, halo->epoch, halo->d_counters);
+  else
+    halo_wait_unpack_kernel<float><<<(int)b, kThreads, 0, stream>>>(
+        (float*)u, d.dofs, d.row_ptr, d.src, d.num_dofs, (const float*)recv,
+        flags, halo->d_peer_ranks, d.num_peers, halo->epoch, halo->d_counters);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_halo_timed_out(const sfem_halo* halo, sfem_stream_t stream) {
+  using namespace sfem;
+  SFEM_REQUIRE(halo, "null argument");
+  unsigned v = 0;
+  SFEM_CUDA_CHECK(cudaMemcpyAsync(&v, halo->d_counters + 4, sizeof(v),
+                                  cudaMemcpyDeviceToHost,
+                                  (cudaStream_t)stream));
+  SFEM_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  return v != 0 ? 1 : 0;
+}
+
+int sfem_op_apply_halo(const sfem_op* op, sfem_halo* halo, double lambda,
+                       double mu, const void* x, void* y,
+                       int64_t num_interface_elements, void* dot_xy,
+                       sfem_stream_t stream_) {
+  using namespace sfem;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SFEM_REQUIRE(op && halo && x && y, "null argument");
+  SFEM_REQUIRE(x != y, "sfem_op_apply_halo is out of place");
+  const sfem_space_desc& d = op->base.desc;
+  SFEM_REQUIRE(d.dtype == halo->desc.dtype, "operator / halo dtype mismatch");
+  SFEM_REQUIRE(num_interface_elements >= 0 &&
+                   num_interface_elements <= d.num_elements,
+               "num_interface_elements out of range");
+  SFEM_REQUIRE(lambda == 0.0 || op->with_mass,
+               "operator was created without mass factors but lambda != 0");
+  const bool fused = op->variant == 0 && d.collocated && d.dim == 3 &&
+                     d.n1d >= 2 && d.n1d <= 16 && d.num_elements > 0;
+  if (!fused) {
+    int rc = op_apply_internal(op, lambda, mu, x, y, 1, (double*)dot_xy, stream);
+    if (rc) return rc;
+    return sfem_halo_push(halo, y, stream_);
+  }
+  const size_t esz = d.dtype == SFEM_F64 ? 8 : 4;
+  if (op->n_zero > 0)
+    SFEM_CUDA_CHECK(cudaMemsetAsync(y, 0, esz * (size_t)op->n_zero, stream));
+  if (dot_xy) SFEM_CUDA_CHECK(cudaMemsetAsync(dot_xy, 0, sizeof(double), stream));
+  const HaloDev hd = begin_epoch(halo, num_interface_elements);
+  sfem_op sub = *op;
+  sub.fuse = &hd;
+  return d.dtype == SFEM_F64
+             ? launch_apply3d_halo<double>(sub, lambda, mu, x, y,
+                                           (double*)dot_xy, stream)
+             : launch_apply3d_halo<float>(sub, lambda, mu, x, y,
+                                          (double*)dot_xy, stream);
+}
+
+}  // extern "C"

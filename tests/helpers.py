@@ -67,3 +67,18 @@ def deformed_premesh(ndim, ne, n1d, seed=None, periodic_dims=(), curved=True,
   if curved and not periodic_dims:
     refined = refined.replace(node_coords=deform(refined.node_coords))
   return refined
+
+
+def local_to_global(global_coords, local_coords):
+  """Index of every local node in the global mesh, matched through the
+  (undeformed) coordinates."""
+  ndim = global_coords.shape[1]
+  key = lambda c: np.round(np.asarray(c) * 1e9).astype(np.int64)  # noqa: E731
+  gk, lk = key(global_coords), key(local_coords)
+  order = np.lexsort(gk.T[::-1])
+  rec = [('', np.int64)] * ndim
+  view_g = np.ascontiguousarray(gk[order]).view(rec).ravel()
+  view_l = np.ascontiguousarray(lk).view(rec).ravel()
+  l2g = order[np.searchsorted(view_g, view_l)]
+  assert np.array_equal(gk[l2g], lk)
+  return l2g

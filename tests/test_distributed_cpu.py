@@ -174,3 +174,58 @@ def test_plan_from_reference_partition_golden():
       shared_local = np.unique(np.concatenate(
           [plan.local_idx[q] for q in plan.peers])) if plan.peers else []
       np.testing.assert_array_equal(np.sort(gi[r][gi[r] >= 0]), shared_local)
+
+
+@pytest.mark.parametrize('case', [(3, 4, 5, 8), (3, 2, 8, 2), (3, 4, 4, 4),
+                                  (2, 8, 4, 4)])
+def test_p2p_tables_route_every_dof_to_its_canonical_slot(case):
+  """Host arithmetic of the peer-memory exchange: every (rank, peer, shared
+  dof) send entry lands in a distinct slot of the peer's receive buffer, and
+  the slot is the one the peer's canonical sum reads for that dof."""
+  from swirl_fem_b200.communication import partition as part
+  from swirl_fem_b200.communication.halo import p2p_region_layout, p2p_tables
+  from swirl_fem_b200.core.interpolation import Nodes1D, NodeType
+  ndim, ne, n1d, world = case
+  g = Nodes1D.create(n1d, NodeType.GAUSS_LOBATTO_LEGENDRE)
+  blks = [part.block_partition(ne, ndim, g, r, world) for r in range(world)]
+  gathered = [np.sort(b.interface_global) for b in blks]
+  plans = [part.halo_plan_from_interfaces(
+      r, b.interface_local, b.interface_global, gathered, b.premesh.num_nodes)
+           for r, b in enumerate(blks)]
+  all_splits = [p.splits() for p in plans]
+  esz = 8
+  flag_bytes, stride, total = p2p_region_layout(
+      world, max(sum(s) for s in all_splits), esz)
+  assert flag_bytes % 256 == 0 and stride % 256 == 0
+  assert total == flag_bytes + 2 * stride
+  bases = {q: (q + 1) << 32 for q in range(world)}
+  gid = [dict(zip(b.interface_local.tolist(), b.interface_global.tolist()))
+         for b in blks]
+  recv = {q: np.full(sum(all_splits[q]), -1, dtype=np.int64)
+          for q in range(world)}
+  for r, p in enumerate(plans):
+    dst, flag_addr = p2p_tables(
+        r, p.peers, {q: len(v) for q, v in p.local_idx.items()}, all_splits,
+        bases, esz)
+    assert [int(a) for a in flag_addr] == [bases[q] + 8 * r for q in p.peers]
+    off = 0
+    for q in p.peers:
+      n = len(p.local_idx[q])
+      slots = (dst[off:off + n].astype(np.int64) - bases[q] - flag_bytes) // esz
+      assert slots.min() >= 0 and slots.max() < len(recv[q])
+      assert (recv[q][slots] == -1).all()
+      recv[q][slots] = [gid[r][int(l)] for l in p.local_idx[q]]
+      off += n
+  for q, p in enumerate(plans):
+    assert (recv[q] >= 0).all()
+    dofs, row_ptr, src = p.canonical_csr()
+    for i, d in enumerate(dofs):
+      for j in range(row_ptr[i], row_ptr[i + 1]):
+        if src[j] >= 0:
+          assert recv[q][src[j]] == gid[q][int(d)]
+
+
+def test_p2p_tables_reject_inconsistent_counts():
+  from swirl_fem_b200.communication.halo import p2p_tables
+  with pytest.raises(ValueError, match='disagree'):
+    p2p_tables(0, [1], {1: 5}, [[0, 5], [4, 0]], {1: 1 << 20}, 8)

@@ -556,6 +556,90 @@ def test_cg_building_blocks_match_fused_solver():
   assert i3['num_iterations'] == 4
 
 
+@pytest.mark.parametrize('case', [(3, 4, 5, 8), (3, 2, 8, 2), (3, 4, 4, 4),
+                                  (2, 8, 4, 4)],
+                         ids=lambda c: f'{c[0]}d_ne{c[1]}_N{c[2]}_w{c[3]}')
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+def test_peer_memory_halo_single_process(case, dtype):
+  """All ranks' blocks on ONE GPU: the fused apply + in-kernel push (3-D), the
+  standalone push (2-D) and the wait + canonical sum, against the
+  unpartitioned operator.  Only CUDA IPC and real concurrency are left to
+  tools/check_multi_gpu.py."""
+  from swirl_fem_b200.common.premesh_commons import unit_cube_mesh
+  from swirl_fem_b200.communication import partition as part
+  from swirl_fem_b200.communication.halo import HaloPlan
+  from swirl_fem_b200.core.interpolation import Nodes1D, Quadrature1D
+  from swirl_fem_b200.core.mesh import Mesh
+  from swirl_fem_b200.core.mesh_refiner import refine_premesh
+  from swirl_fem_b200.core.operator import FusedOperator
+  from tests.helpers import local_to_global
+  ndim, ne, n1d, world = case
+  device = torch.device('cuda', 0)
+  grid1d = Nodes1D.create(n1d, GLL)
+  quad = Quadrature1D.create_from_nodes_1d(grid1d)
+  blks = [part.block_partition(ne, ndim, grid1d, r, world)
+          for r in range(world)]
+  gathered = [np.sort(b.interface_global) for b in blks]
+  plans = [part.halo_plan_from_interfaces(
+      r, b.interface_local, b.interface_global, gathered, b.premesh.num_nodes)
+           for r, b in enumerate(blks)]
+  HaloPlan.enable_p2p_local(plans, dtype, device)
+  field = lambda x: np.cos(1.3 * x[:, 0]) * (1 + .5 * x[:, -1]) + .2 * x[:, 1] ** 2  # noqa: E731
+  bench_deform = lambda x: x + 0.08 * np.sin(  # noqa: E731
+      np.pi * x[:, np.roll(np.arange(ndim), 1)]) * (1 - x ** 2)
+  ops, us, ys, dots = [], [], [], []
+  for b in blks:
+    x0 = b.premesh.node_coords
+    mesh = Mesh.create(bench_deform(x0), b.premesh.elements,
+                       gridpoints_1d=grid1d, device=device, dtype=dtype)
+    ops.append(FusedOperator(mesh, quad, dirichlet_mask=b.dirichlet,
+                             with_mass=True))
+    us.append(torch.as_tensor(field(x0)).to(device=device, dtype=dtype))
+    ys.append(torch.empty_like(us[-1]))
+    dots.append(torch.zeros((), dtype=torch.float64, device=device))
+  ref = refine_premesh(unit_cube_mesh(ne, ndim=ndim, a=-1., b=1.), grid1d)
+  gmesh = Mesh.create(bench_deform(ref.node_coords), ref.elements,
+                      gridpoints_1d=grid1d, device=device, dtype=dtype)
+  bmask = ref.finalize_host()['physical_masks']['boundary']
+  gop = FusedOperator(gmesh, quad, dirichlet_mask=bmask, with_mass=True)
+  gu = torch.as_tensor(field(ref.node_coords)).to(device=device, dtype=dtype)
+  tol = 1e-12 if dtype == torch.float64 else 2e-5
+  for epoch, (lam, mu) in enumerate([(0.3, 1.0), (0.0, 1.0), (1.0, 0.5)]):
+    gy = gop.apply(gu, lam=lam, mu=mu).cpu().numpy()
+    # every rank's apply + push first (a push never waits), then the waits
+    for r in range(world):
+      ops[r].apply_partitioned(us[r], ys[r], plans[r],
+                               blks[r].num_interface_elements, lam=lam, mu=mu,
+                               dot_out=dots[r], wait=False)
+    for r in range(world):
+      plans[r].p2p_wait_unpack(ys[r])
+    torch.cuda.synchronize()
+    total_dot = 0.0
+    for r in range(world):
+      assert not plans[r].p2p_timed_out(device)
+      l2g = local_to_global(ref.node_coords, blks[r].premesh.node_coords)
+      err = np.abs(ys[r].cpu().numpy() - gy[l2g]).max() / np.abs(gy).max()
+      assert err < tol, (epoch, r, err)
+      total_dot += float(dots[r])
+    want_dot = float((gu.double() * torch.as_tensor(gy).to(device).double()
+                      ).sum())
+    assert abs(total_dot - want_dot) <= (1e-11 if dtype == torch.float64
+                                         else 1e-4) * abs(want_dot)
+  # exchange_ of a plain vector through the same handles (push + wait):
+  # multiplicity of every dof = number of ranks holding it
+  ones = [torch.ones_like(u) for u in us]
+  for r in range(world):
+    plans[r].p2p_push(ones[r])
+  for r in range(world):
+    plans[r].p2p_wait_unpack(ones[r])
+  mult = np.zeros(ref.num_nodes)
+  l2gs = [local_to_global(ref.node_coords, b.premesh.node_coords) for b in blks]
+  for l2g in l2gs:
+    mult[l2g] += 1
+  for r in range(world):
+    assert np.array_equal(ones[r].cpu().numpy(), mult[l2gs[r]])
+
+
 def test_multi_gpu_partitioned_parity():
   """2 ranks over NCCL vs the unpartitioned solve (needs >= 2 GPUs)."""
   import os

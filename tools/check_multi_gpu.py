@@ -74,6 +74,24 @@ def main():
     torch.cuda.synchronize()
     assert float((y2 - y).abs().max()) <= 1e-13 * float(y.abs().max()), (
         'overlapped apply differs from apply + exchange')
+    # peer-memory path (CUDA IPC + NVLink stores): fused apply + in-kernel
+    # push (3-D) / apply + push kernel (2-D), then wait + canonical sum
+    p2p = os.environ.get('SFEM_HALO', 'p2p') == 'p2p' and halo.enable_p2p(
+        torch.float64, dev)
+    if p2p:
+      for rep in range(3):   # both epoch parities
+        y3 = torch.empty_like(y)
+        dot3 = torch.zeros((), dtype=torch.float64, device=dev)
+        op.apply_partitioned(u, y3, halo, blk.num_interface_elements, lam=0.3,
+                             mu=1.0, dot_out=dot3)
+        torch.cuda.synchronize()
+        assert not halo.p2p_timed_out(dev), 'peer flag wait timed out'
+        assert float((y3 - y).abs().max()) <= 1e-13 * float(y.abs().max()), (
+            f'peer-memory apply differs from apply + NCCL exchange (rep {rep}):'
+            f' {float((y3 - y).abs().max())}')
+        assert abs(float(dot3) - float(dot2)) <= 1e-12 * abs(float(dot2))
+    if rank == 0:
+      print(f'  halo path: {"peer memory (P2P)" if p2p else "NCCL"}', flush=True)
     # ---- unpartitioned reference on this GPU
     ref = refine_premesh(unit_cube_mesh(ne, ndim=ndim, a=-1., b=1.), grid1d)
     gmesh = Mesh.create(deform(ref.node_coords), ref.elements,
@@ -113,6 +131,7 @@ def main():
     it_ok = abs(info['num_iterations'] - ginfo['num_iterations']) <= 1
     good = err < 1e-12 and berr < 1e-12 and xerr < 1e-7 and it_ok
     ok = ok and good
+    halo.disable_p2p()
     print(f'[rank {rank}/{world}] {ndim}-D ne={ne} N={n1d}: apply err {err:.1e} '
           f'rhs err {berr:.1e} cg x err {xerr:.1e} iters '
           f'{info["num_iterations"]} vs {ginfo["num_iterations"]} '
