@@ -296,6 +296,13 @@ int sfem_op_apply_halo(const sfem_op* op, sfem_halo* halo, double lambda,
 /* 1 if the last wait of this handle timed out (peer never raised its flag). */
 int sfem_halo_timed_out(const sfem_halo* halo, sfem_stream_t stream);
 
+/* Diagnostics of the last fused apply (host array of 8 globaltimer stamps in
+ * ns, synchronises): [0] kernel start, [1] CTA 0 past its interface
+ * elements, [2] CTA 0 saw all CTAs past theirs, [3] CTA 0 done pushing,
+ * [4] flags raised on the peers, [5] CTA 0 exit. */
+int sfem_halo_debug_times(const sfem_halo* halo, uint64_t* out8,
+                          sfem_stream_t stream);
+
 /* ------------------------------------------------------------------------ */
 /* CG (swirl_fem/linalg/cg.py:30-97)                                         */
 /* ------------------------------------------------------------------------ */

@@ -105,6 +105,7 @@ SIGNATURES = {
     'sfem_halo_push': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr]),
     'sfem_halo_wait_unpack': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr]),
     'sfem_halo_timed_out': (ctypes.c_int, [_c_ptr, _c_ptr]),
+    'sfem_halo_debug_times': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr]),
     'sfem_op_apply_halo': (ctypes.c_int, [_c_ptr, _c_ptr, _c_f64, _c_f64,
                                           _c_ptr, _c_ptr, _c_i64, _c_ptr,
                                           _c_ptr]),

@@ -353,6 +353,19 @@ class HaloPlan:
       return bool(_lib.lib().sfem_halo_timed_out(p['handle'],
                                                  _lib.stream_ptr(device)))
 
+  def p2p_debug_times(self, device):
+    """us offsets (from the kernel start) of the last fused apply's stamps."""
+    p = getattr(self, '_p2p', None)
+    out = (ctypes.c_uint64 * 8)()
+    with torch.cuda.device(device):
+      _lib._check(_lib.lib().sfem_halo_debug_times(
+          p['handle'], out, _lib.stream_ptr(device)), 'sfem_halo_debug_times')
+    t = [int(v) for v in out]
+    names = ['start', 'cta0_signal', 'cta0_ready', 'cta0_pushed',
+             'flags_raised', 'cta0_exit']
+    return {n: (t[i] - t[0]) / 1e3 if t[i] else None
+            for i, n in enumerate(names)}
+
   def exchange_(self, u: torch.Tensor) -> torch.Tensor:
     """In-place QQ^T on this rank's `(num_local_nodes,)` vector.
 

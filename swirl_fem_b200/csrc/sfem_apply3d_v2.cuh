@@ -315,6 +315,8 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
   // waiting for the other CTAs, 2 pushed
   __shared__ unsigned s_halo[2];
   int hstate = 0;
+  const bool stamp = HALO && blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamp) halo_stamp(hd, 0);
 
   int buf = 0;
   for (; blk < nblocks; blk += gridDim.x, buf ^= 1) {
@@ -359,9 +361,12 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
           atomicAdd(&hd.counters[0], 1u);
         }
         hstate = 1;
+        if (stamp) halo_stamp(hd, 1);
       } else if (hstate == 1 && s_halo[0]) {
+        if (stamp) halo_stamp(hd, 2);
         halo_push_slices<T>(hd, y, &s_halo[1]);
         hstate = 2;
+        if (stamp) halo_stamp(hd, 3);
       }
     }
 
@@ -532,6 +537,7 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       __syncthreads();
       if (s_halo[0]) halo_push_slices<T>(hd, y, &s_halo[1]);
     }
+    if (stamp) halo_stamp(hd, 5);
   }
   if (want_dot) {
     dot = block_sum(dot, red);

@@ -23,7 +23,7 @@ struct sfem_halo {
   sfem_halo_desc desc;
   uint64_t* d_peer_flag = nullptr;  // device copy of desc.peer_flag_addr
   int32_t* d_peer_ranks = nullptr;
-  unsigned* d_counters = nullptr;   // 8 words, see HaloDev::counters
+  unsigned* d_counters = nullptr;   // 24 words, see HaloDev::counters
   uint64_t epoch = 0;
   unsigned slice = 256;
 };
@@ -202,14 +202,14 @@ int sfem_halo_create(const sfem_halo_desc* desc, sfem_halo** halo) {
   const size_t np = (size_t)desc->num_peers;
   cudaError_t e = cudaMalloc(&h->d_peer_flag, np * sizeof(uint64_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->d_peer_ranks, np * sizeof(int32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_counters, 8 * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_counters, 24 * sizeof(unsigned));
   if (e == cudaSuccess)
     e = cudaMemcpy(h->d_peer_flag, desc->peer_flag_addr, np * sizeof(uint64_t),
                    cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
     e = cudaMemcpy(h->d_peer_ranks, desc->peer_ranks, np * sizeof(int32_t),
                    cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(h->d_counters, 0, 24 * sizeof(unsigned));
   if (e != cudaSuccess) {
     set_error(std::string("sfem_halo_create: ") + cudaGetErrorString(e));
     sfem_halo_destroy(h);
@@ -269,6 +269,17 @@ int sfem_halo_timed_out(const sfem_halo* halo, sfem_stream_t stream) {
                                   (cudaStream_t)stream));
   SFEM_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
   return v != 0 ? 1 : 0;
+}
+
+int sfem_halo_debug_times(const sfem_halo* halo, uint64_t* out8,
+                          sfem_stream_t stream) {
+  using namespace sfem;
+  SFEM_REQUIRE(halo && out8, "null argument");
+  SFEM_CUDA_CHECK(cudaMemcpyAsync(out8, halo->d_counters + 8,
+                                  8 * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                  (cudaStream_t)stream));
+  SFEM_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  return SFEM_OK;
 }
 
 int sfem_op_apply_halo(const sfem_op* op, sfem_halo* halo, double lambda,
