@@ -274,6 +274,9 @@ def run_ours(args):
       halo_path = ('peer memory (in-kernel NVLink push)'
                    if halo.enable_p2p(dtype, device) else
                    'nccl all_to_all (peer mapping failed)')
+      if os.environ.get('SFEM_HALO_FUSE_UNPACK', '1') == '0':
+        halo.p2p_set_option(1, 0)
+        halo_path += ', canonical sum in the wait kernel'
     else:
       halo_path = 'nccl all_to_all'
   torch.cuda.synchronize()

@@ -269,13 +269,19 @@ typedef struct sfem_halo sfem_halo;
 int sfem_halo_create(const sfem_halo_desc* desc, sfem_halo** halo);
 void sfem_halo_destroy(sfem_halo* halo);
 
+/* Tuning (call between epochs only).  key 0: entries per work item of the
+ * cooperative push / sum (default 256); key 1: whether the fused apply also
+ * runs the canonical sum inside its kernel (default 1). */
+int sfem_halo_set_option(sfem_halo* halo, int32_t key, int64_t value);
+
 /* Starts a new epoch: u's shared dofs -> the peers' receive buffers, then
  * this rank's flag is raised on every peer.  Never waits. */
 int sfem_halo_push(sfem_halo* halo, const void* u, sfem_stream_t stream);
 
 /* Waits (on the device) for the current epoch's flags of all peers, then
- * u[dof] = sum over all holders in ascending rank order.  Every rank must
- * run the same sequence of push / wait_unpack calls. */
+ * u[dof] = sum over all holders in ascending rank order -- or whatever part
+ * of that sum the fused apply has not already done inside its kernel.  Every
+ * rank must run the same sequence of push / wait_unpack calls. */
 int sfem_halo_wait_unpack(sfem_halo* halo, void* u, sfem_stream_t stream);
 
 /* First half of y = QQ^T (mask . scatter(local_op(gather(x)))) on an
@@ -283,9 +289,12 @@ int sfem_halo_wait_unpack(sfem_halo* halo, void* u, sfem_stream_t stream);
  * the ones touching other ranks' blocks: ONE apply launch that pushes the
  * shared dofs of y to the peers as soon as all interface elements are done,
  * while the interior elements are still being computed (3-D collocated
- * kernels; other kernel families run the apply, then sfem_halo_push).  The
- * caller completes the exchange with sfem_halo_wait_unpack(halo, y) -- work
- * that does not read y's shared dofs may be enqueued in between.  ncomp = 1.
+ * kernels; other kernel families run the apply, then sfem_halo_push).  CTAs
+ * that have pushed poll the peers' flags between element steps and, once all
+ * peers' values are in, also run the canonical sum inside the same kernel.
+ * The caller completes the exchange with sfem_halo_wait_unpack(halo, y),
+ * which waits and does what is left of the sum (usually nothing) -- work that
+ * does not touch y's shared dofs may be enqueued in between.  ncomp = 1.
  * dot_xy as in sfem_op_apply (the local, pre-exchange x . y: element-wise
  * partial sums need no ownership weights). */
 int sfem_op_apply_halo(const sfem_op* op, sfem_halo* halo, double lambda,
@@ -299,7 +308,8 @@ int sfem_halo_timed_out(const sfem_halo* halo, sfem_stream_t stream);
 /* Diagnostics of the last fused apply (host array of 8 globaltimer stamps in
  * ns, synchronises): [0] kernel start, [1] CTA 0 past its interface
  * elements, [2] CTA 0 saw all CTAs past theirs, [3] CTA 0 done pushing,
- * [4] flags raised on the peers, [5] CTA 0 exit. */
+ * [4] flags raised on the peers, [5] CTA 0 exit, [6] CTA 0 saw all peers'
+ * flags, [7] CTA 0 done with its share of the canonical sum. */
 int sfem_halo_debug_times(const sfem_halo* halo, uint64_t* out8,
                           sfem_stream_t stream);
 

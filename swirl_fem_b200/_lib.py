@@ -102,6 +102,7 @@ SIGNATURES = {
     'sfem_halo_create': (ctypes.c_int, [ctypes.POINTER(HaloDesc),
                                         ctypes.POINTER(_c_ptr)]),
     'sfem_halo_destroy': (None, [_c_ptr]),
+    'sfem_halo_set_option': (ctypes.c_int, [_c_ptr, _c_i32, _c_i64]),
     'sfem_halo_push': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr]),
     'sfem_halo_wait_unpack': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr]),
     'sfem_halo_timed_out': (ctypes.c_int, [_c_ptr, _c_ptr]),

@@ -333,6 +333,13 @@ class HaloPlan:
       return None
     return p['handle']
 
+  def p2p_set_option(self, key: int, value: int):
+    """0: slice size, 1: fuse the canonical sum into the apply kernel."""
+    p = getattr(self, '_p2p', None)
+    if p is not None:
+      _lib._check(_lib.lib().sfem_halo_set_option(p['handle'], key, value),
+                  'sfem_halo_set_option')
+
   def p2p_push(self, u: torch.Tensor):
     with torch.cuda.device(u.device):
       _lib._check(_lib.lib().sfem_halo_push(
@@ -362,7 +369,7 @@ class HaloPlan:
           p['handle'], out, _lib.stream_ptr(device)), 'sfem_halo_debug_times')
     t = [int(v) for v in out]
     names = ['start', 'cta0_signal', 'cta0_ready', 'cta0_pushed',
-             'flags_raised', 'cta0_exit']
+             'flags_raised', 'cta0_exit', 'cta0_peers_ready', 'cta0_unpacked']
     return {n: (t[i] - t[0]) / 1e3 if t[i] else None
             for i, n in enumerate(names)}
 

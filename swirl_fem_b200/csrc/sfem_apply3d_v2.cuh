@@ -213,10 +213,13 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc,
 // counter; once every CTA has, the shared dofs of y are final on this rank and
 // the CTAs push them (slice by slice, between two element steps) straight into
 // the peers' receive buffers over NVLink while the interior elements are still
-// being computed -- the exchange costs no extra launch and no wire time on
-// the critical path.  Nothing ever spins: a CTA that exits before the counter
-// completes leaves its slices to the CTAs that are still running (the last
-// signaller always is).
+// being computed.  After its push a CTA polls the peers' flags between element
+// steps; once all peers' values have arrived the CTAs also run the canonical
+// sum of the shared dofs (no interior element touches them), so in the usual
+// lock-step case the whole exchange is hidden and the wait kernel that follows
+// finds nothing left to do.  Nothing ever spins: a CTA that exits before a
+// condition holds leaves its slices to the CTAs that are still running (the
+// last signaller always is) or, for the sum, to the wait kernel.
 template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH,
           bool HALO = false>
 __global__ void __launch_bounds__((Cfg3DV2<T, N, EPB, MINB, KCH>::threads),
@@ -313,8 +316,14 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
 
   // HALO state (block-uniform): 0 interface steps pending, 1 signalled and
   // waiting for the other CTAs, 2 pushed
-  __shared__ unsigned s_halo[2];
+  __shared__ unsigned s_halo[3];  // [0] ready to push, [1] slice, [2] peers late
   int hstate = 0;
+  uint64_t hpend = 0;  // this thread's poll in flight (state 2)
+  unsigned hiter = 0;  // element steps spent in state 2
+  // ... and its address (computed once: the poll must be ONE independent load)
+  const void* hpoll = &hd.counters[2];
+  if (HALO && threadIdx.x < hd.num_peers)
+    hpoll = hd.flags + hd.peer_ranks[threadIdx.x];
   const bool stamp = HALO && blockIdx.x == 0 && threadIdx.x == 0;
   if (stamp) halo_stamp(hd, 0);
 
@@ -345,8 +354,26 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       }
     }
 
-    if (HALO && threadIdx.x == 0)
-      s_halo[0] = hstate == 1 && ld_acquire_gpu(&hd.counters[0]) >= gridDim.x;
+    if (HALO) {
+      if (hstate == 1) {
+        if (threadIdx.x == 0)
+          s_halo[0] = ld_acquire_gpu(&hd.counters[0]) >= gridDim.x;
+      } else if (hstate == 2 && (hiter < 8 || (hiter & 3) == 0) &&
+                 threadIdx.x <= hd.num_peers) {
+        // Pushed; waiting for the peers' values.  Thread k polls peer k's flag
+        // (the thread after the last peer: this rank's count of completed
+        // push slices, after which y's shared dofs are no longer read).  The
+        // poll is software-pipelined: a load issued here is looked at one
+        // element step later, so a late peer costs nothing but these few
+        // instructions (every step at first, every fourth step after eight).
+        const bool is_flag = threadIdx.x < hd.num_peers;
+        if (hpend < (is_flag ? hd.epoch : (uint64_t)hd.num_slices))
+          s_halo[2] = 1;  // not yet
+        hpend = is_flag ? ld_relaxed_sys(reinterpret_cast<const uint64_t*>(hpoll))
+                        : (uint64_t)ld_relaxed_gpu(
+                              reinterpret_cast<const unsigned*>(hpoll));
+      }
+    }
 
     // ---- u tile of this element has landed (cp.async issued one element ago)
     cp_async_wait_all();
@@ -364,9 +391,19 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
         if (stamp) halo_stamp(hd, 1);
       } else if (hstate == 1 && s_halo[0]) {
         if (stamp) halo_stamp(hd, 2);
-        halo_push_slices<T>(hd, y, &s_halo[1]);
-        hstate = 2;
+        halo_push_slices<T>(hd, y, &s_halo[1], 1);
+        hstate = hd.fuse_unpack ? 2 : 3;
+        hiter = 0;
         if (stamp) halo_stamp(hd, 3);
+      } else if (hstate == 2 && (hiter < 8 || (hiter & 3) == 0) &&
+                 s_halo[2] == 0) {
+        // all peers' values have arrived: canonical sum of the shared dofs
+        // (no interior element touches them), also hidden under the interior
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        if (stamp) halo_stamp(hd, 6);
+        halo_unpack_slices<T>(hd, y, &s_halo[1], 1);
+        hstate = 3;
+        if (stamp) halo_stamp(hd, 7);
       }
     }
 
@@ -385,6 +422,11 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       for (int j = 0; j < N; ++j) sB[baseC + (SWZ ? (j ^ qs) : j)] = out[j];
     }
     __syncthreads();
+
+    if (HALO && hstate == 2) {
+      if (threadIdx.x == 0) s_halo[2] = 0;
+      ++hiter;
+    }
 
     // ---- issue the gather of the next element into the other u tile (its
     //      previous contents were last read before the barrier above)
@@ -535,7 +577,17 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       if (threadIdx.x == 0)
         s_halo[0] = ld_acquire_gpu(&hd.counters[0]) >= gridDim.x;
       __syncthreads();
-      if (s_halo[0]) halo_push_slices<T>(hd, y, &s_halo[1]);
+      if (s_halo[0]) {
+        halo_push_slices<T>(hd, y, &s_halo[1]);
+        hstate = hd.fuse_unpack ? 2 : 3;
+      }
+    }
+    if (hstate == 2) {
+      // one last look; what is left is done by the wait kernel
+      __syncthreads();
+      if (threadIdx.x == 0) s_halo[0] = halo_peers_ready(hd);
+      __syncthreads();
+      if (s_halo[0]) halo_unpack_slices<T>(hd, y, &s_halo[1]);
     }
     if (stamp) halo_stamp(hd, 5);
   }
@@ -574,11 +626,23 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
   fill_even_odd<T, N>(op.base.h_BD, true, &dm.bwd);
   HaloDev hd{};
   if (HALO) {
-    if (op.fuse == nullptr || ncomp != 1) {
-      set_error("fused halo push needs a halo and ncomp == 1");
+    if (op.fuse == nullptr || ncomp != 1 || op.fuse->num_peers >= 32) {
+      set_error("fused halo push needs a halo with < 32 peers and ncomp == 1");
       return SFEM_ERR_INVALID;
     }
-    hd = *op.fuse;  // n_if_blocks arrives as an ELEMENT count
+    // one work item per CTA (at least 32 entries): n_if_blocks arrives as an
+    // ELEMENT count
+    HaloDev& f = *op.fuse;
+    auto size_for = [&](int64_t total) {
+      int64_t per = (total + grid.x - 1) / grid.x;
+      per = ((per + 31) / 32) * 32;
+      return (unsigned)(per < 32 ? 32 : per);
+    };
+    f.slice = size_for(f.num_send);
+    f.num_slices = (unsigned)((f.num_send + f.slice - 1) / f.slice);
+    f.uslice = size_for(f.num_dofs);
+    f.num_uslices = (unsigned)((f.num_dofs + f.uslice - 1) / f.uslice);
+    hd = f;
     hd.n_if_blocks = (hd.n_if_blocks + C::epb - 1) / C::epb;
   }
   kernel<<<grid, C::threads, smem, stream>>>(

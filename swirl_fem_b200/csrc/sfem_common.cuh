@@ -108,10 +108,12 @@ __device__ __forceinline__ T ld_stream(const T* p) {
   return __ldcs(p);
 }
 
-// ---- peer-memory halo push (shared by the fused apply and sfem_halo_push) -------
-// Everything the device side of a push needs; filled per call by the host
-// (`sfem_halo` handle, sfem_halo.cu) and passed to kernels by value.
+// ---- peer-memory halo exchange (device side, shared by the fused apply and the
+//      standalone kernels of sfem_halo.cu) ------------------------------------------
+// Everything the device side needs; filled per call by the host (`sfem_halo`
+// handle, sfem_halo.cu) and passed to kernels by value.
 struct HaloDev {
+  // send side
   const int32_t* send_idx;    // (num_send) local dof of every send entry
   const uint64_t* send_dst;   // (num_send) address of the entry's slot in the
                               // peer's receive buffer of parity 0
@@ -122,11 +124,23 @@ struct HaloDev {
   uint64_t flag_parity_off;   // byte offset of this epoch's flag words
   int num_peers;
   unsigned num_slices;        // ceil(num_send / slice)
-  unsigned slice;             // send entries per work item
+  unsigned slice;             // send entries per push work item
+  unsigned uslice;            // shared dofs per canonical-sum work item
+  // receive side (canonical sum, see sfem_halo_unpack_canonical)
+  unsigned num_uslices;       // ceil(num_dofs / slice)
+  int fuse_unpack;            // fused apply: also run the canonical sum
+  const uint64_t* flags;      // this rank's flag words of this epoch's parity
+  const int32_t* peer_ranks;  // (num_peers)
+  const void* recv;           // this epoch's receive buffer
+  const int32_t* dofs;
+  const int32_t* row_ptr;
+  const int32_t* src;
+  int64_t num_dofs;
   unsigned* counters;         // [0] CTAs past the interface elements,
-                              // [1] next slice, [2] slices done, [3] unpack
-                              // CTAs done, [4] wait timed out; words 8..23:
-                              // eight 64-bit globaltimer stamps (diagnostics)
+                              // [1] next push slice, [2] push slices done,
+                              // [3] wait-kernel CTAs done, [4] wait timed out,
+                              // [5] next unpack slice; words 8..23: eight
+                              // 64-bit globaltimer stamps (diagnostics)
   uint64_t epoch;
   int64_t n_if_blocks;        // CTA steps that cover the interface elements
 };
@@ -136,9 +150,19 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
   uint64_t v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t ld_relaxed_sys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
@@ -157,10 +181,14 @@ __device__ __forceinline__ void halo_stamp(const HaloDev& h, int slot) {
 // CTA that completes the last slice raises this rank's flag on every peer
 // (release at system scope, after every writer fenced its stores).
 // `y` values were produced by other CTAs (RED / stores): read them from L2.
+// `max_slices`: how many slices this call may take (the fused apply takes ONE
+// per element step so that no CTA donates more time than the others: with a
+// static element partition the kernel ends with its slowest CTA).
 template <typename T>
 __device__ __forceinline__ void halo_push_slices(const HaloDev& h, const T* y,
-                                                 unsigned* s_slice) {
-  for (;;) {
+                                                 unsigned* s_slice,
+                                                 unsigned max_slices = ~0u) {
+  for (unsigned it = 0; it < max_slices; ++it) {
     __syncthreads();
     if (threadIdx.x == 0) *s_slice = atomicAdd(&h.counters[1], 1u);
     __syncthreads();
@@ -184,6 +212,49 @@ __device__ __forceinline__ void halo_push_slices(const HaloDev& h, const T* y,
                          h.epoch);
         halo_stamp(h, 4);
       }
+    }
+  }
+}
+
+// One thread: have all of this rank's push slices completed (y's shared dofs
+// are no longer read) AND has every peer raised its flag of this epoch?  The
+// polls are relaxed; a positive answer is followed by a system-scope fence so
+// that the receive buffers may be read afterwards.
+__device__ __forceinline__ bool halo_peers_ready(const HaloDev& h) {
+  bool ok = ld_relaxed_gpu(&h.counters[2]) >= h.num_slices;
+  for (int k = 0; k < h.num_peers; ++k)
+    ok = ok && ld_relaxed_sys(h.flags + h.peer_ranks[k]) >= h.epoch;
+  if (ok) __threadfence_system();
+  return ok;
+}
+
+// Cooperative canonical sum (block-uniform, like halo_push_slices):
+// y[dof] = sum over all holders in ascending rank order; src < 0 stands for
+// this rank's own value.  Precondition: halo_peers_ready() was observed (by a
+// thread of this CTA before a barrier, or by the wait kernel).
+template <typename T>
+__device__ __forceinline__ void halo_unpack_slices(const HaloDev& h, T* y,
+                                                   unsigned* s_slice,
+                                                   unsigned max_slices = ~0u) {
+  const T* recv = reinterpret_cast<const T*>(h.recv);
+  for (unsigned it = 0; it < max_slices; ++it) {
+    __syncthreads();
+    if (threadIdx.x == 0) *s_slice = atomicAdd(&h.counters[5], 1u);
+    __syncthreads();
+    const unsigned s = *s_slice;
+    if (s >= h.num_uslices) break;
+    const int64_t b = (int64_t)s * h.uslice;
+    const int64_t e = b + h.uslice < h.num_dofs ? b + h.uslice : h.num_dofs;
+    for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+      const int32_t d = __ldg(h.dofs + i);
+      const T own = __ldcg(y + d);
+      T acc = T(0);
+      const int32_t j1 = __ldg(h.row_ptr + i + 1);
+      for (int32_t j = __ldg(h.row_ptr + i); j < j1; ++j) {
+        const int32_t sj = __ldg(h.src + j);
+        acc += sj < 0 ? own : __ldcg(recv + sj);
+      }
+      y[d] = acc;
     }
   }
 }
@@ -241,6 +312,7 @@ struct sfem_op {
   int64_t n_zero;   // y[0 .. n_zero) must be zeroed before an apply
   int variant;      // 0 auto, 1 generic
   // set on a shallow copy by sfem_op_apply_halo: fuse the halo push into the
-  // apply kernel (interface elements first)
-  const sfem::HaloDev* fuse = nullptr;
+  // apply kernel (interface elements first).  The launcher sizes the work
+  // items for its grid (fields slice / uslice / num_slices / num_uslices).
+  sfem::HaloDev* fuse = nullptr;
 };

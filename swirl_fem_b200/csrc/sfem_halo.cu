@@ -25,7 +25,9 @@ struct sfem_halo {
   int32_t* d_peer_ranks = nullptr;
   unsigned* d_counters = nullptr;   // 24 words, see HaloDev::counters
   uint64_t epoch = 0;
-  unsigned slice = 256;
+  unsigned slice = 256;      // default work-item size (standalone kernels)
+  unsigned cur_uslice = 256; // canonical-sum work-item size of this epoch
+  int fuse_unpack = 1;
 };
 
 namespace sfem {
@@ -50,74 +52,83 @@ halo_push_kernel(const T* __restrict__ y, const __grid_constant__ HaloDev hd) {
 }
 
 // Spins (bounded: ~4 s of globaltimer) until every peer raised its flag of
-// this epoch, then runs the canonical sum.  The last CTA to finish resets the
-// handle's counters for the next epoch.
+// this epoch, then runs whatever is left of the canonical sum (nothing, when
+// the fused apply already did it).  The last CTA to finish resets the handle's
+// counters for the next epoch.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-halo_wait_unpack_kernel(T* __restrict__ u, const int32_t* __restrict__ dofs,
-                        const int32_t* __restrict__ row_ptr,
-                        const int32_t* __restrict__ src, int64_t num_dofs,
-                        const T* recv, const uint64_t* flags,
-                        const int32_t* __restrict__ peer_ranks, int num_peers,
-                        uint64_t epoch, unsigned* counters) {
-  for (int k = threadIdx.x; k < num_peers; k += blockDim.x) {
-    const uint64_t* f = flags + peer_ranks[k];
-    uint64_t t0 = 0;
-    unsigned spins = 0;
-    while (ld_acquire_sys(f) < epoch) {
-      if ((++spins & 1023u) == 0) {
-        uint64_t now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t0 == 0) t0 = now;
-        if (now - t0 > 4000000000ull) {
-          atomicExch(&counters[4], 1u);
-          break;
+halo_wait_unpack_kernel(T* __restrict__ u, const __grid_constant__ HaloDev hd) {
+  __shared__ unsigned s_slice;
+  // other CTAs claim slices concurrently: one thread decides for the CTA
+  if (threadIdx.x == 0) s_slice = ld_relaxed_gpu(&hd.counters[5]);
+  __syncthreads();
+  if (s_slice < hd.num_uslices) {
+    for (int k = threadIdx.x; k < hd.num_peers; k += blockDim.x) {
+      const uint64_t* f = hd.flags + hd.peer_ranks[k];
+      uint64_t t0 = 0;
+      unsigned spins = 0;
+      while (ld_acquire_sys(f) < hd.epoch) {
+        if ((++spins & 1023u) == 0) {
+          uint64_t now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          if (now - t0 > 4000000000ull) {
+            atomicExch(&hd.counters[4], 1u);
+            break;
+          }
         }
       }
     }
-  }
-  __syncthreads();
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < num_dofs;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int32_t d = dofs[i];
-    const T own = u[d];
-    T acc = T(0);
-    for (int32_t j = row_ptr[i]; j < row_ptr[i + 1]; ++j) {
-      const int32_t s = src[j];
-      acc += s < 0 ? own : __ldcg(recv + s);
-    }
-    u[d] = acc;
+    halo_unpack_slices<T>(hd, u, &s_slice);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned done = atomicAdd(&counters[3], 1u) + 1u;
+    const unsigned done = atomicAdd(&hd.counters[3], 1u) + 1u;
     if (done == gridDim.x) {
-      counters[0] = 0;
-      counters[1] = 0;
-      counters[2] = 0;
-      counters[3] = 0;
+      hd.counters[0] = 0;
+      hd.counters[1] = 0;
+      hd.counters[2] = 0;
+      hd.counters[3] = 0;
+      hd.counters[5] = 0;
       __threadfence();
     }
   }
 }
 
-HaloDev begin_epoch(sfem_halo* h, int64_t num_interface_elements) {
-  h->epoch += 1;
+// Device view of the handle for its CURRENT epoch.
+HaloDev device_view(const sfem_halo* h, int64_t num_interface_elements) {
+  const sfem_halo_desc& d = h->desc;
   const unsigned parity = (unsigned)(h->epoch & 1u);
   HaloDev hd{};
-  hd.send_idx = h->desc.send_idx;
-  hd.send_dst = h->desc.send_dst;
-  hd.num_send = h->desc.num_send;
-  hd.parity_off = parity ? h->desc.parity_stride_bytes : 0;
+  hd.send_idx = d.send_idx;
+  hd.send_dst = d.send_dst;
+  hd.num_send = d.num_send;
+  hd.parity_off = parity ? d.parity_stride_bytes : 0;
   hd.peer_flag = h->d_peer_flag;
-  hd.flag_parity_off = parity ? (uint64_t)h->desc.world * 8u : 0u;
-  hd.num_peers = h->desc.num_peers;
+  hd.flag_parity_off = parity ? (uint64_t)d.world * 8u : 0u;
+  hd.num_peers = d.num_peers;
   hd.slice = h->slice;
-  hd.num_slices = (unsigned)((h->desc.num_send + h->slice - 1) / h->slice);
+  hd.num_slices = (unsigned)((d.num_send + h->slice - 1) / h->slice);
+  hd.uslice = h->cur_uslice;
+  hd.num_uslices = (unsigned)((d.num_dofs + hd.uslice - 1) / hd.uslice);
+  hd.fuse_unpack = h->fuse_unpack;
+  hd.flags = d.flags + (parity ? d.world : 0);
+  hd.peer_ranks = h->d_peer_ranks;
+  hd.recv = (const char*)d.recv + (parity ? d.parity_stride_bytes : 0);
+  hd.dofs = d.dofs;
+  hd.row_ptr = d.row_ptr;
+  hd.src = d.src;
+  hd.num_dofs = d.num_dofs;
   hd.counters = h->d_counters;
   hd.epoch = h->epoch;
   hd.n_if_blocks = num_interface_elements;
   return hd;
+}
+
+HaloDev begin_epoch(sfem_halo* h, int64_t num_interface_elements) {
+  h->epoch += 1;
+  h->cur_uslice = h->slice;
+  return device_view(h, num_interface_elements);
 }
 
 int push_standalone(sfem_halo* h, const HaloDev& hd, const void* u,
@@ -229,6 +240,23 @@ void sfem_halo_destroy(sfem_halo* halo) {
   delete halo;
 }
 
+int sfem_halo_set_option(sfem_halo* halo, int32_t key, int64_t value) {
+  using namespace sfem;
+  SFEM_REQUIRE(halo, "null argument");
+  switch (key) {
+    case 0:
+      SFEM_REQUIRE(value >= 32 && value <= (1 << 20), "slice out of range");
+      halo->slice = (unsigned)value;
+      return SFEM_OK;
+    case 1:
+      halo->fuse_unpack = value != 0;
+      return SFEM_OK;
+    default:
+      set_error("sfem_halo_set_option: unknown key");
+      return SFEM_ERR_INVALID;
+  }
+}
+
 int sfem_halo_push(sfem_halo* halo, const void* u, sfem_stream_t stream) {
   using namespace sfem;
   SFEM_REQUIRE(halo && u, "null argument");
@@ -242,20 +270,20 @@ int sfem_halo_wait_unpack(sfem_halo* halo, void* u, sfem_stream_t stream_) {
   SFEM_REQUIRE(halo && u, "null argument");
   SFEM_REQUIRE(halo->epoch > 0, "wait_unpack before the first push");
   const sfem_halo_desc& d = halo->desc;
-  const unsigned parity = (unsigned)(halo->epoch & 1u);
-  const uint64_t* flags = d.flags + (parity ? d.world : 0);
-  const char* recv = (const char*)d.recv + (parity ? d.parity_stride_bytes : 0);
-  int64_t b = (d.num_dofs + kThreads - 1) / kThreads;
-  const int64_t cap = (int64_t)num_sms() * 4;
+  const HaloDev hd = device_view(halo, 0);
+  // sized for the case that the whole sum is still to do (one slice per CTA,
+  // at most 2 CTAs per SM); when the fused apply already did it the CTAs
+  // return at once
+  int64_t b = hd.num_uslices;
+  const int64_t cap = (int64_t)num_sms() * 2;
   if (b > cap) b = cap;
+  if (b < 1) b = 1;
   if (d.dtype == SFEM_F64)
-    halo_wait_unpack_kernel<double><<<(int)b, kThreads, 0, stream>>>(
-        (double*)u, d.dofs, d.row_ptr, d.src, d.num_dofs, (const double*)recv,
-        flags, halo->d_peer_ranks, d.num_peers, halo->epoch, halo->d_counters);
+    halo_wait_unpack_kernel<double><<<(int)b, kThreads, 0, stream>>>((double*)u,
+                                                                     hd);
   else
-    halo_wait_unpack_kernel<float><<<(int)b, kThreads, 0, stream>>>(
-        (float*)u, d.dofs, d.row_ptr, d.src, d.num_dofs, (const float*)recv,
-        flags, halo->d_peer_ranks, d.num_peers, halo->epoch, halo->d_counters);
+    halo_wait_unpack_kernel<float><<<(int)b, kThreads, 0, stream>>>((float*)u,
+                                                                    hd);
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }
@@ -298,7 +326,8 @@ int sfem_op_apply_halo(const sfem_op* op, sfem_halo* halo, double lambda,
   SFEM_REQUIRE(lambda == 0.0 || op->with_mass,
                "operator was created without mass factors but lambda != 0");
   const bool fused = op->variant == 0 && d.collocated && d.dim == 3 &&
-                     d.n1d >= 2 && d.n1d <= 16 && d.num_elements > 0;
+                     d.n1d >= 2 && d.n1d <= 16 && d.num_elements > 0 &&
+                     halo->desc.num_peers < 32;
   if (!fused) {
     int rc = op_apply_internal(op, lambda, mu, x, y, 1, (double*)dot_xy, stream);
     if (rc) return rc;
@@ -308,14 +337,16 @@ int sfem_op_apply_halo(const sfem_op* op, sfem_halo* halo, double lambda,
   if (op->n_zero > 0)
     SFEM_CUDA_CHECK(cudaMemsetAsync(y, 0, esz * (size_t)op->n_zero, stream));
   if (dot_xy) SFEM_CUDA_CHECK(cudaMemsetAsync(dot_xy, 0, sizeof(double), stream));
-  const HaloDev hd = begin_epoch(halo, num_interface_elements);
+  HaloDev hd = begin_epoch(halo, num_interface_elements);
   sfem_op sub = *op;
-  sub.fuse = &hd;
-  return d.dtype == SFEM_F64
-             ? launch_apply3d_halo<double>(sub, lambda, mu, x, y,
-                                           (double*)dot_xy, stream)
-             : launch_apply3d_halo<float>(sub, lambda, mu, x, y,
-                                          (double*)dot_xy, stream);
+  sub.fuse = &hd;  // the launcher sizes the work items for its grid
+  const int rc = d.dtype == SFEM_F64
+                     ? launch_apply3d_halo<double>(sub, lambda, mu, x, y,
+                                                   (double*)dot_xy, stream)
+                     : launch_apply3d_halo<float>(sub, lambda, mu, x, y,
+                                                  (double*)dot_xy, stream);
+  halo->cur_uslice = hd.uslice;
+  return rc;
 }
 
 }  // extern "C"

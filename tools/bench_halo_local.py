@@ -83,14 +83,22 @@ def main():
     for r in range(2):
       ops[r].apply(xs[r], out=ys[r])
   if world == 2:
-    t2 = timed(plain2)
-    tf = timed(fused)
-    tu = timed(unfused)
-    fused()
-    torch.cuda.synchronize()
-    print('stamps (us from kernel start):', plans[0].p2p_debug_times(dev))
-    print(f'plain apply rank0 {t_plain:.1f} us; both ranks plain {t2:.1f} us; '
-          f'fused+wait {tf:.1f} us; apply+push+wait {tu:.1f} us')
+    import itertools
+    res = {}
+    for rnd, mode in itertools.product(range(2), ('plain', 'fused',
+                                                  'fused_nounpack', 'unfused')):
+      for pl in plans:
+        pl.p2p_set_option(1, 0 if mode == 'fused_nounpack' else 1)
+      fn = {'plain': plain2, 'fused': fused, 'fused_nounpack': fused,
+            'unfused': unfused}[mode]
+      res.setdefault(mode, []).append(timed(fn))
+      if mode.startswith('fused') and rnd == 0:
+        fn()
+        torch.cuda.synchronize()
+        for r in range(2):
+          print(mode, 'rank', r, 'stamps (us):', plans[r].p2p_debug_times(dev))
+    print(f'plain apply rank0 {t_plain:.1f} us; both ranks: ' + '; '.join(
+        f'{k} {min(v):.1f}' for k, v in res.items()))
 
 
 if __name__ == '__main__':
