@@ -314,13 +314,21 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
   }
   cp_async_commit();
 
-  // HALO state (block-uniform): 0 interface steps pending, 1 signalled and
-  // waiting for the other CTAs, 2 pushed
+  // HALO state machine (block-uniform), advanced between element steps
+  enum : int {
+    kHIface = 0,   // interface steps of this CTA pending
+    kHSignal = 1,  // signalled; waiting for the other CTAs' interface steps
+    kHIssued = 2,  // one push slice issued (loads + remote stores in flight)
+    kHFenced = 3,  // ... fenced and counted; the ticket is in flight
+    kHPoll = 4,    // pushed; polling the peers' flags
+    kHDone = 5
+  };
   __shared__ unsigned s_halo[3];  // [0] ready to push, [1] slice, [2] peers late
-  int hstate = 0;
-  uint64_t hpend = 0;  // this thread's poll in flight (state 2)
-  unsigned hiter = 0;  // element steps spent in state 2
-  // ... and its address (computed once: the poll must be ONE independent load)
+  int hstate = kHIface;
+  uint64_t hpend = 0;    // this thread's poll in flight (kHPoll)
+  unsigned hiter = 0;    // element steps spent in kHPoll
+  unsigned hticket = 0;  // thread 0: this CTA's slice was the hticket-th done
+  // the poll must be ONE independent load: its address is computed once
   const void* hpoll = &hd.counters[2];
   if (HALO && threadIdx.x < hd.num_peers)
     hpoll = hd.flags + hd.peer_ranks[threadIdx.x];
@@ -355,17 +363,21 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     }
 
     if (HALO) {
-      if (hstate == 1) {
+      if (hstate == kHSignal) {
         if (threadIdx.x == 0)
           s_halo[0] = ld_acquire_gpu(&hd.counters[0]) >= gridDim.x;
-      } else if (hstate == 2 && (hiter < 8 || (hiter & 3) == 0) &&
+      } else if (hstate == kHFenced) {
+        // the ticket of this CTA's slice has arrived: the last one raises
+        // this rank's flags on the peers
+        if (threadIdx.x == 0 && hticket == hd.num_slices) halo_raise_flags(hd);
+      } else if (hstate == kHPoll && (hiter < 8 || (hiter & 3) == 0) &&
                  threadIdx.x <= hd.num_peers) {
-        // Pushed; waiting for the peers' values.  Thread k polls peer k's flag
-        // (the thread after the last peer: this rank's count of completed
-        // push slices, after which y's shared dofs are no longer read).  The
-        // poll is software-pipelined: a load issued here is looked at one
-        // element step later, so a late peer costs nothing but these few
-        // instructions (every step at first, every fourth step after eight).
+        // Waiting for the peers' values.  Thread k polls peer k's flag (the
+        // thread after the last peer: this rank's count of completed push
+        // slices, after which y's shared dofs are no longer read).  The poll
+        // is software-pipelined: a load issued here is looked at one element
+        // step later, so a late peer costs nothing but these few instructions
+        // (every step at first, every fourth step after eight).
         const bool is_flag = threadIdx.x < hd.num_peers;
         if (hpend < (is_flag ? hd.epoch : (uint64_t)hd.num_slices))
           s_halo[2] = 1;  // not yet
@@ -380,29 +392,35 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     __syncthreads();
 
     if (HALO) {
-      if (hstate == 0 && blk >= hd.n_if_blocks) {
+      if (hstate == kHIface && blk >= hd.n_if_blocks) {
         // every thread fenced its y updates at the end of the last interface
         // step and has passed the barrier above
         if (threadIdx.x == 0) {
           __threadfence();
           atomicAdd(&hd.counters[0], 1u);
         }
-        hstate = 1;
+        hstate = kHSignal;
         if (stamp) halo_stamp(hd, 1);
-      } else if (hstate == 1 && s_halo[0]) {
+      } else if (hstate == kHSignal && s_halo[0]) {
         if (stamp) halo_stamp(hd, 2);
-        halo_push_slices<T>(hd, y, &s_halo[1], 1);
-        hstate = hd.fuse_unpack ? 2 : 3;
-        hiter = 0;
+        hstate = halo_push_issue<T>(hd, y, &s_halo[1])
+                     ? kHIssued
+                     : (hd.fuse_unpack ? kHPoll : kHDone);
         if (stamp) halo_stamp(hd, 3);
-      } else if (hstate == 2 && (hiter < 8 || (hiter & 3) == 0) &&
+      } else if (hstate == kHIssued) {
+        // the remote stores were issued a whole element step ago
+        __threadfence_system();
+        hstate = kHFenced;  // counted after the next barrier
+      } else if (hstate == kHFenced) {
+        hstate = hd.fuse_unpack ? kHPoll : kHDone;
+      } else if (hstate == kHPoll && (hiter < 8 || (hiter & 3) == 0) &&
                  s_halo[2] == 0) {
         // all peers' values have arrived: canonical sum of the shared dofs
         // (no interior element touches them), also hidden under the interior
         asm volatile("fence.acq_rel.sys;" ::: "memory");
         if (stamp) halo_stamp(hd, 6);
         halo_unpack_slices<T>(hd, y, &s_halo[1], 1);
-        hstate = 3;
+        hstate = kHDone;
         if (stamp) halo_stamp(hd, 7);
       }
     }
@@ -423,9 +441,16 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     }
     __syncthreads();
 
-    if (HALO && hstate == 2) {
-      if (threadIdx.x == 0) s_halo[2] = 0;
-      ++hiter;
+    if (HALO) {
+      if (hstate == kHFenced && hticket == 0) {
+        // all threads' fences precede the barrier above.  (hticket == 0: the
+        // state is entered before this point and left after the next step's
+        // first barrier, so it passes here exactly once.)
+        if (threadIdx.x == 0) hticket = atomicAdd(&hd.counters[2], 1u) + 1u;
+      } else if (hstate == kHPoll) {
+        if (threadIdx.x == 0) s_halo[2] = 0;
+        ++hiter;
+      }
     }
 
     // ---- issue the gather of the next element into the other u tile (its
@@ -560,29 +585,43 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     active = active_n;
 #pragma unroll
     for (int k = 0; k < N; ++k) rc[k] = nrc[k];
-    if (HALO && hstate == 0 && blk_n >= hd.n_if_blocks) __threadfence();
+    if (HALO && hstate == kHIface && blk_n >= hd.n_if_blocks) __threadfence();
   }
   cp_async_wait_all();
   if (HALO) {
-    if (hstate == 0) {  // all steps of this CTA were interface steps
+    // finish whatever is in flight; from here on the blocking forms are used
+    if (hstate == kHIssued) {
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) hticket = atomicAdd(&hd.counters[2], 1u) + 1u;
+      hstate = kHFenced;
+    } else if (hstate == kHFenced && hticket == 0) {
+      // (cannot happen: the count is taken in the step the state is entered)
+      if (threadIdx.x == 0) hticket = atomicAdd(&hd.counters[2], 1u) + 1u;
+    }
+    if (hstate == kHFenced) {
+      if (threadIdx.x == 0 && hticket == hd.num_slices) halo_raise_flags(hd);
+      hstate = hd.fuse_unpack ? kHPoll : kHDone;
+    }
+    if (hstate == kHIface) {  // all steps of this CTA were interface steps
       __syncthreads();
       if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(&hd.counters[0], 1u);
       }
-      hstate = 1;
+      hstate = kHSignal;
     }
-    if (hstate == 1) {
+    if (hstate == kHSignal) {
       __syncthreads();
       if (threadIdx.x == 0)
         s_halo[0] = ld_acquire_gpu(&hd.counters[0]) >= gridDim.x;
       __syncthreads();
       if (s_halo[0]) {
         halo_push_slices<T>(hd, y, &s_halo[1]);
-        hstate = hd.fuse_unpack ? 2 : 3;
+        hstate = hd.fuse_unpack ? kHPoll : kHDone;
       }
     }
-    if (hstate == 2) {
+    if (hstate == kHPoll) {
       // one last look; what is left is done by the wait kernel
       __syncthreads();
       if (threadIdx.x == 0) s_halo[0] = halo_peers_ready(hd);
@@ -619,8 +658,13 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
     if (per_sm < 1) per_sm = 1;
   }
   // persistent CTAs: one wave, every CTA pipelines over its elements
+  // ... and the wave is trimmed so that every CTA gets the same number of
+  // steps (+-1): with 39 304 steps on 888 slots a quarter of the CTAs would
+  // run a 45th step while the others idle; 874 CTAs x 45 steps do not
   const int64_t cap = (int64_t)num_sms() * per_sm;
-  dim3 grid((unsigned)(nblocks < cap ? nblocks : cap), ncomp);
+  const int64_t steps_per_cta = (nblocks + cap - 1) / cap;
+  const int64_t even = (nblocks + steps_per_cta - 1) / steps_per_cta;
+  dim3 grid((unsigned)(nblocks < cap ? nblocks : even), ncomp);
   DOps<T, N> dm;
   fill_even_odd<T, N>(op.base.h_BD, false, &dm.fwd);
   fill_even_odd<T, N>(op.base.h_BD, true, &dm.bwd);
@@ -669,9 +713,10 @@ struct AutoCfg3D {
       staged ? stage_bytes : (long)C0::stage_off(EPB) * (long)sizeof(T);
   static constexpr int by_smem =
       (int)((220L * 1024) / (smem_bytes > 0 ? smem_bytes : 1));
-  // register estimate fitted to ptxas output (fp64: 114 @ N=5 ... 180 @ N=9)
+  // register estimate fitted to ptxas output (fp64: 114 @ N=5 ... 180 @ N=9;
+  // fp32: 66 @ N=5, 93 @ N=9, 118 @ N=12)
   static constexpr int est_regs_raw =
-      sizeof(T) == 8 ? 26 + 17 * N : 40 + 9 * N;
+      sizeof(T) == 8 ? 26 + 17 * N : (60 + 15 * N) / 2;
   static constexpr int est_regs = est_regs_raw > 255 ? 255 : est_regs_raw;
   static constexpr int by_regs = 65536 / (C0::threads * est_regs);
   static constexpr int m0 = by_smem < by_regs ? by_smem : by_regs;

@@ -175,6 +175,17 @@ __device__ __forceinline__ void halo_stamp(const HaloDev& h, int slot) {
   reinterpret_cast<uint64_t*>(h.counters + 8)[slot] = now;
 }
 
+// One thread, after ALL push slices are complete and fenced: raise this
+// rank's flag of the epoch on every peer (release at system scope).
+__device__ __forceinline__ void halo_raise_flags(const HaloDev& h) {
+  __threadfence_system();
+  for (int k = 0; k < h.num_peers; ++k)
+    st_release_sys(
+        reinterpret_cast<uint64_t*>(h.peer_flag[k] + h.flag_parity_off),
+        h.epoch);
+  halo_stamp(h, 4);
+}
+
 // Cooperative push of the shared dofs into the peers' receive buffers (P2P
 // stores over NVLink).  Called by ALL threads of a CTA (block-uniform); CTAs
 // draw slices of the send list from a global counter until none is left.  The
@@ -205,15 +216,33 @@ __device__ __forceinline__ void halo_push_slices(const HaloDev& h, const T* y,
     if (threadIdx.x == 0) {
       const unsigned done = atomicAdd(&h.counters[2], 1u) + 1u;
       if (done == h.num_slices) {
-        __threadfence_system();
-        for (int k = 0; k < h.num_peers; ++k)
-          st_release_sys(reinterpret_cast<uint64_t*>(h.peer_flag[k] +
-                                                     h.flag_parity_off),
-                         h.epoch);
-        halo_stamp(h, 4);
+        halo_raise_flags(h);
       }
     }
   }
+}
+
+// Split form of one push work item for the fused apply: claim a slice and
+// issue its loads and remote stores WITHOUT waiting for them (no fence).  The
+// caller fences one element step later (the stores have long been
+// acknowledged by then), counts the slice as done after the next barrier and
+// raises the flags if it was the last one.  Returns false when no slice was
+// left.  Block-uniform.
+template <typename T>
+__device__ __forceinline__ bool halo_push_issue(const HaloDev& h, const T* y,
+                                                unsigned* s_slice) {
+  __syncthreads();
+  if (threadIdx.x == 0) *s_slice = atomicAdd(&h.counters[1], 1u);
+  __syncthreads();
+  const unsigned s = *s_slice;
+  if (s >= h.num_slices) return false;
+  const int64_t b = (int64_t)s * h.slice;
+  const int64_t e = b + h.slice < h.num_send ? b + h.slice : h.num_send;
+  for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+    const T v = __ldcg(y + __ldg(h.send_idx + i));
+    *reinterpret_cast<T*>(__ldg(h.send_dst + i) + h.parity_off) = v;
+  }
+  return true;
 }
 
 // One thread: have all of this rank's push slices completed (y's shared dofs
