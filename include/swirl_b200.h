@@ -153,6 +153,19 @@ int sfem_space_eval(const sfem_space* space, const void* u_local,
                     int32_t ncomp, int32_t kind, void* out,
                     sfem_stream_t stream);
 
+/* Transpose of sfem_space_eval: the local covector of a functional that is
+ * linear in a placeholder function v, which the reference obtains with
+ * jax.linear_transpose of the quadrature integral (fespace.py:458-471):
+ *   out[e,n,c] = sum_q W[q] jacdets[e,q] ( vals[e,q,c] phi_n(q)
+ *                + sum_j grads[e,q,j,c] d phi_n / d x_j (q) )
+ * vals: (E, Q^d, ncomp) coefficient of v_c's value, or NULL; grads:
+ * (E, Q^d, d, ncomp) coefficient of d v_c / d x_j, or NULL; out:
+ * (E, N^d, ncomp).  Used for the mixed velocity / pressure forms of the
+ * Stokes solver (D, D^T, convection; navier_stokes.py:238-245, 313-338). */
+int sfem_space_eval_transpose(const sfem_space* space, const void* vals,
+                              const void* grads, int32_t ncomp, void* out,
+                              sfem_stream_t stream);
+
 /* FiniteElementSpace.integrate (fespace.py:381-403):
  * *result = sum_{e,q} w[e,q] * jacdets[e,q] * W[q].  result: device fp64
  * scalar (always double, zeroed by the call). */

@@ -142,7 +142,8 @@ def vmap(fn, in_axes=0, out_axes=0, axis_name=None):
     for i in range(size):
       sliced = [
           a if ax is None else _tree_map(
-              lambda leaf, ax=ax: np.take(np.asarray(leaf), i, axis=ax), a)
+              lambda leaf, ax=ax: _wrap(np.take(np.asarray(leaf), i,
+                                                axis=ax)), a)
           for a, ax in zip(args, axes)
       ]
       skw = {k: _tree_map(lambda leaf: np.asarray(leaf)[i], v)

@@ -116,6 +116,8 @@ SIGNATURES = {
     'sfem_space_destroy': (None, [_c_ptr]),
     'sfem_space_eval': (ctypes.c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr,
                                        _c_ptr]),
+    'sfem_space_eval_transpose': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr,
+                                                 _c_i32, _c_ptr, _c_ptr]),
     'sfem_space_integrate': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr]),
     'sfem_op_geom_bytes': (_c_i64, [ctypes.POINTER(SpaceDesc), _c_i32]),
     'sfem_op_conn_bytes': (_c_i64, [ctypes.POINTER(SpaceDesc)]),

@@ -58,6 +58,9 @@ class NodalQFunction:
   u_local: torch.Tensor | None = None
   # classification probe: (value, gradient) returned instead of an evaluation
   _probe: tuple | None = dataclasses.field(default=None, repr=False)
+  # evaluations shared by a function and its gradient while a form is probed
+  # several times (general `local_covector` path)
+  _memo: dict | None = dataclasses.field(default=None, repr=False)
 
   def __post_init__(self):
     expected = (self.fespace.num_elements,
@@ -76,15 +79,20 @@ class NodalQFunction:
     del x  # nodal values, not coordinates, define the function
     if self._probe is not None:
       return self._probe_value()
+    if self._memo is not None and type(self) in self._memo:
+      return self._memo[type(self)]
     out = self._evaluate()
     extra = out.dim() - 2
-    return out.permute(*range(2, 2 + extra), 0, 1) if extra else out
+    out = out.permute(*range(2, 2 + extra), 0, 1) if extra else out
+    if self._memo is not None:
+      self._memo[type(self)] = out
+    return out
 
 
 class ScalarNodalQFunction(NodalQFunction):
 
-  def __init__(self, fespace, u_local=None, _probe=None):
-    super().__init__(fespace, (), u_local, _probe)
+  def __init__(self, fespace, u_local=None, _probe=None, _memo=None):
+    super().__init__(fespace, (), u_local, _probe, _memo)
 
   def _evaluate(self):
     return self.fespace._eval(self.u_local, ncomp=1, kind=0)
@@ -95,8 +103,8 @@ class ScalarNodalQFunction(NodalQFunction):
 
 class ScalarNodalQFunctionGrad(NodalQFunction):
 
-  def __init__(self, fespace, u_local=None, _probe=None):
-    super().__init__(fespace, (), u_local, _probe)
+  def __init__(self, fespace, u_local=None, _probe=None, _memo=None):
+    super().__init__(fespace, (), u_local, _probe, _memo)
 
   def _evaluate(self):
     return self.fespace._eval(self.u_local, ncomp=1, kind=1)
@@ -107,8 +115,8 @@ class ScalarNodalQFunctionGrad(NodalQFunction):
 
 class VectorNodalQFunction(NodalQFunction):
 
-  def __init__(self, fespace, u_local=None, _probe=None):
-    super().__init__(fespace, (fespace.mesh.ndim,), u_local, _probe)
+  def __init__(self, fespace, u_local=None, _probe=None, _memo=None):
+    super().__init__(fespace, (fespace.mesh.ndim,), u_local, _probe, _memo)
 
   def _evaluate(self):
     return self.fespace._eval(self.u_local, ncomp=self.fespace.mesh.ndim,
@@ -120,8 +128,8 @@ class VectorNodalQFunction(NodalQFunction):
 
 class VectorNodalQFunctionGrad(NodalQFunction):
 
-  def __init__(self, fespace, u_local=None, _probe=None):
-    super().__init__(fespace, (fespace.mesh.ndim,), u_local, _probe)
+  def __init__(self, fespace, u_local=None, _probe=None, _memo=None):
+    super().__init__(fespace, (fespace.mesh.ndim,), u_local, _probe, _memo)
 
   def _evaluate(self):
     # (E, q, d, d) with [..., j, k] = d u_k / d x_j (fespace.py:224-225)
@@ -147,9 +155,9 @@ def _autograd_gradient(f: Callable) -> Callable:
 def grad(f: QFunction) -> QFunction:
   """Gradient of a q-function."""
   if isinstance(f, ScalarNodalQFunction):
-    return ScalarNodalQFunctionGrad(f.fespace, f.u_local, f._probe)
+    return ScalarNodalQFunctionGrad(f.fespace, f.u_local, f._probe, f._memo)
   if isinstance(f, VectorNodalQFunction):
-    return VectorNodalQFunctionGrad(f.fespace, f.u_local, f._probe)
+    return VectorNodalQFunctionGrad(f.fespace, f.u_local, f._probe, f._memo)
   return _autograd_gradient(f)
 
 
@@ -419,8 +427,103 @@ class FiniteElementSpace:
     Equivalent to the reference's `jax.linear_transpose` of the integral
     (:458-471) for the Helmholtz family of forms; see the module docstring.
     """
-    fc = _classify(form, funs, self)
+    try:
+      fc = _classify(form, funs, self)
+    except (NotImplementedError, TypeError):
+      # not of the Helmholtz family (or written with tensor-only operations)
+      return self._general_covector(form, funs)
     u_local = funs[fc.data_index].u_local
     op = self.operator(None, with_mass=True)
     ncomp = 1 if fc.kind == 'scalar' else self.mesh.ndim
     return op.apply_local(u_local, lam=fc.lam, mu=fc.mu, ncomp=ncomp)
+
+  def _eval_transpose(self, vals, grads, ncomp: int) -> torch.Tensor:
+    """Transpose of `_eval` through the C ABI (`sfem_space_eval_transpose`)."""
+    e, n = self.num_elements, self.mesh.num_nodes_per_element
+    dev = self.mesh.device
+    shape = (e, n) if ncomp == 1 else (e, n, ncomp)
+    out = torch.empty(shape, dtype=self.dtype, device=dev)
+    with torch.cuda.device(dev):
+      _lib._check(_lib.lib().sfem_space_eval_transpose(
+          self._handle.handle, _lib.ptr(vals), _lib.ptr(grads), ncomp,
+          _lib.ptr(out), _lib.stream_ptr(dev)), 'sfem_space_eval_transpose')
+    return out
+
+  def _general_covector(self, form: Form, funs) -> torch.Tensor:
+    """`local_covector` for any form that is linear in its placeholder.
+
+    The reference transposes the quadrature integral with
+    `jax.linear_transpose` (:458-471).  Here the form is evaluated on the
+    quadrature points with the placeholder's value / gradient set to each unit
+    direction in turn (data functions are evaluated once, by the CUDA
+    evaluation kernels, and memoised); that yields the pointwise coefficients
+    of `v` and `grad v`, which `sfem_space_eval_transpose` contracts with the
+    weighted basis functions.  Mixed-space forms (Stokes `D`, `D^T`:
+    navier_stokes.py:313-338) and trilinear ones (convection, :238-245) take
+    this path; data functions of another space must share this space's
+    quadrature rule.
+    """
+    is_dual = [isinstance(f, NodalQFunction) and f.u_local is None
+               for f in funs]
+    dual_index = is_dual.index(True)
+    dual = funs[dual_index]
+    if dual.fespace is not self:
+      raise ValueError('the placeholder function must belong to this space')
+    e, q, d = self.num_elements, self.num_quadrature_points_per_element, (
+        self.mesh.ndim)
+    dev, dtype = self.mesh.device, self.dtype
+    for f in funs:
+      if isinstance(f, NodalQFunction) and f.u_local is not None:
+        fq = f.fespace.num_quadrature_points_per_element
+        if f.fespace.num_elements != e or fq != q:
+          raise ValueError(
+              'data functions must live on the same elements and quadrature '
+              f'points as the placeholder: got {(f.fespace.num_elements, fq)} '
+              f'vs {(e, q)}')
+    vector = isinstance(dual, VectorNodalQFunction)
+    nv = d if vector else 1
+    cls = VectorNodalQFunction if vector else ScalarNodalQFunction
+    x = self.quad_coords.permute(2, 0, 1)
+    memos = {}
+    for f in funs:
+      if (isinstance(f, NodalQFunction) and f.u_local is not None
+          and id(f) not in memos):
+        memos[id(f)] = (f, f._memo)
+        f._memo = {}
+
+    def probe(value, gradient):
+      args = list(funs)
+      args[dual_index] = cls(self, None, (value, gradient))
+      out = form(*args)(x)
+      if not isinstance(out, torch.Tensor):
+        out = torch.as_tensor(float(out), dtype=dtype, device=dev)
+      return out.to(dtype).expand(e, q)
+
+    def unit(shape, index):
+      t = torch.zeros(shape + (1, 1), dtype=dtype, device=dev)
+      if index is not None:
+        t[index] = 1.0
+      return t
+
+    vshape = (d,) if vector else ()
+    gshape = (d, d) if vector else (d,)
+    try:
+      vals = torch.stack(
+          [probe(unit(vshape, (k,) if vector else ()), unit(gshape, None))
+           for k in range(nv)], dim=-1)                       # (E, q, nv)
+      grads = torch.stack([
+          torch.stack(
+              [probe(unit(vshape, None),
+                     unit(gshape, (j, k) if vector else (j,)))
+               for k in range(nv)], dim=-1)
+          for j in range(d)], dim=-2)                         # (E, q, d, nv)
+    finally:
+      for f, old in memos.values():
+        f._memo = old
+    vals = vals.contiguous() if bool(vals.any()) else None
+    grads = grads.contiguous() if bool(grads.any()) else None
+    if vals is None and grads is None:
+      n = self.mesh.num_nodes_per_element
+      return torch.zeros((e, n) + ((d,) if vector else ()), dtype=dtype,
+                         device=dev)
+    return self._eval_transpose(vals, grads, nv)

@@ -21,6 +21,9 @@ template <typename T>
 int launch_eval(const SpaceBase&, const void*, int, int, const void*, void*,
                 cudaStream_t);
 template <typename T>
+int launch_eval_transpose(const SpaceBase&, const void*, const void*, int,
+                          const void*, const void*, void*, cudaStream_t);
+template <typename T>
 int launch_integrate(const SpaceBase&, const void*, const void*, double*,
                      cudaStream_t);
 template <typename T>
@@ -198,6 +201,24 @@ int sfem_space_eval(const sfem_space* space, const void* u_local, int32_t ncomp,
                                    space->invjacs, out, (cudaStream_t)stream)
              : launch_eval<float>(space->base, u_local, ncomp, kind,
                                   space->invjacs, out, (cudaStream_t)stream);
+}
+
+int sfem_space_eval_transpose(const sfem_space* space, const void* vals,
+                              const void* grads, int32_t ncomp, void* out,
+                              sfem_stream_t stream) {
+  using namespace sfem;
+  SFEM_REQUIRE(space && out, "null argument");
+  SFEM_REQUIRE(ncomp >= 1 && ncomp <= 65535, "bad ncomp");
+  SFEM_REQUIRE(space->jacdets != nullptr, "the covector needs jacdets");
+  SFEM_REQUIRE(grads == nullptr || space->invjacs != nullptr,
+               "gradient coefficients need invjacs");
+  return space->base.desc.dtype == SFEM_F64
+             ? launch_eval_transpose<double>(space->base, vals, grads, ncomp,
+                                             space->invjacs, space->jacdets,
+                                             out, (cudaStream_t)stream)
+             : launch_eval_transpose<float>(space->base, vals, grads, ncomp,
+                                            space->invjacs, space->jacdets,
+                                            out, (cudaStream_t)stream);
 }
 
 int sfem_space_integrate(const sfem_space* space, const void* w, void* result,

@@ -300,6 +300,69 @@ eval_kernel(GenShape s, const T* __restrict__ gtab,
 }
 
 // ---------------------------------------------------------------------------
+// Transpose of K2-K4: the local covector of a functional that is linear in a
+// placeholder function v (reference: jax.linear_transpose of the quadrature
+// integral, swirl_fem/core/fespace.py:458-471).  Given the pointwise
+// coefficients of v's value and of its physical gradient,
+//   y[n] = sum_q W_q detJ_q ( a[q] phi_n(q) + sum_j b[q][j] d phi_n / d x_j (q) )
+// a: (E, Q^d, ncomp) or null; b: (E, Q^d, d, ncomp) or null; y: (E, N^d, ncomp).
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kGenericThreads)
+eval_transpose_kernel(GenShape s, const T* __restrict__ gtab,
+                      const T* __restrict__ a, const T* __restrict__ b,
+                      int ncomp, const T* __restrict__ invjacs,
+                      const T* __restrict__ jacdets, int64_t E,
+                      T* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* smem = reinterpret_cast<T*>(smem_raw);
+  GenTables<T> tb;
+  load_tables(s, gtab, smem, &tb);
+  const int d = s.dim;
+  const int tmax = ipow(max(s.N, s.Q), d);
+  T* Y = smem + table_elems(s.N, s.Q);  // (n)
+  T* H = Y + s.n;                       // (q) one weighted coefficient field
+  T* t0 = H + s.q;
+  T* t1 = t0 + tmax;
+  const int c = blockIdx.y;
+
+  for (int64_t e = blockIdx.x; e < E; e += gridDim.x) {
+    for (int i = threadIdx.x; i < s.n; i += blockDim.x) Y[i] = T(0);
+    __syncthreads();
+    // part -1: value coefficient; part i >= 0: reference-gradient axis i
+    for (int part = (a ? -1 : 0); part < (b ? d : 0); ++part) {
+      for (int p = threadIdx.x; p < s.q; p += blockDim.x) {
+        const int64_t eq = e * s.q + p;
+        const T w = quad_weight<T>(s, tb.W, p) * jacdets[eq];
+        T h;
+        if (part < 0) {
+          h = a[eq * ncomp + c];
+        } else {
+          // d phi / d x_j = sum_i Jinv[j][i] d phi / d xi_i
+          const T* inv = invjacs + eq * d * d;
+          h = T(0);
+          for (int j = 0; j < d; ++j)
+            h += b[(eq * d + j) * ncomp + c] * inv[j * d + part];
+        }
+        H[p] = w * h;
+      }
+      __syncthreads();
+      const T* mats[3];
+      bool ident[3];
+      for (int axis = 0; axis < d; ++axis) {
+        const bool deriv = axis == part;
+        mats[axis] = deriv ? tb.BD : tb.B;
+        ident[axis] = !deriv && s.collocated;
+      }
+      backward<T>(s, mats, ident, H, Y, t0, t1);
+    }
+    for (int i = threadIdx.x; i < s.n; i += blockDim.x)
+      out[(e * s.n + i) * ncomp + c] = Y[i];
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
 // K5: integration
 // ---------------------------------------------------------------------------
 template <typename T>
@@ -585,6 +648,28 @@ int launch_eval(const SpaceBase& b, const void* u_local, int ncomp, int kind,
 }
 
 template <typename T>
+int launch_eval_transpose(const SpaceBase& b, const void* a, const void* bg,
+                          int ncomp, const void* invjacs, const void* jacdets,
+                          void* out, cudaStream_t stream) {
+  const GenShape s = make_shape(b);
+  const int d = s.dim;
+  const int tmax = ipow_host(s.N > s.Q ? s.N : s.Q, d);
+  const size_t elems =
+      table_elems(s.N, s.Q) + s.n + (size_t)s.q + 2 * (size_t)tmax;
+  const size_t bytes = elems * sizeof(T);
+  int rc = prepare_smem(eval_transpose_kernel<T>, bytes);
+  if (rc) return rc;
+  const int64_t E = b.desc.num_elements;
+  if (E == 0) return SFEM_OK;
+  dim3 grid(grid_for(E, 4), ncomp);
+  eval_transpose_kernel<T><<<grid, kGenericThreads, bytes, stream>>>(
+      s, tables<T>(b), (const T*)a, (const T*)bg, ncomp, (const T*)invjacs,
+      (const T*)jacdets, E, (T*)out);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+template <typename T>
 int launch_integrate(const SpaceBase& b, const void* w, const void* jacdets,
                      double* result, cudaStream_t stream) {
   const GenShape s = make_shape(b);
@@ -657,6 +742,9 @@ int launch_diag_generic(const sfem_op& op, double lambda, double mu,
                               int, int, cudaStream_t);                         \
   template int launch_eval<T>(const SpaceBase&, const void*, int, int,         \
                               const void*, void*, cudaStream_t);               \
+  template int launch_eval_transpose<T>(const SpaceBase&, const void*,         \
+                                        const void*, int, const void*,         \
+                                        const void*, void*, cudaStream_t);     \
   template int launch_integrate<T>(const SpaceBase&, const void*, const void*, \
                                    double*, cudaStream_t);                     \
   template int launch_apply_generic<T>(const sfem_op&, double, double,         \

@@ -82,3 +82,54 @@ def local_to_global(global_coords, local_coords):
   l2g = order[np.searchsorted(view_g, view_l)]
   assert np.array_equal(gk[l2g], lk)
   return l2g
+
+
+# -- Stokes / Navier-Stokes fixtures (navier_stokes_test.py:39-68) ---------------
+
+
+def stokes_vortices_premesh(ne=9, curved=0.0):
+  """Uniform premesh on [-1, 1] x [-pi, pi], periodic in y
+  (`_make_stokes_vortices_premesh`, navier_stokes_test.py:39-44); `curved`
+  bends the element columns (keeps the y-periodicity)."""
+  pm = unit_cube_mesh(ne, ndim=2, periodic_dims=(1,))
+  x = np.asarray(pm.node_coords, dtype=np.float64)
+  x = np.stack([2 * x[:, 0] - 1, 2 * np.pi * x[:, 1] - np.pi], -1)
+  if curved:
+    x[:, 0] += curved * np.sin(x[:, 1]) * (1 - x[:, 0] ** 2)
+  return pm.replace(node_coords=x)
+
+
+def stokes_oracle_meshes(premesh, order):
+  """Host meshes (numpy) of the velocity (GLL) and pressure (GL) spaces for
+  `oracle.dense_ns.StokesSEM`, built with the host mesh code that the
+  connectivity goldens pin bit-exactly to the reference."""
+  vref = refine_premesh(premesh, Nodes1D.create(order + 1, GLL))
+  pref = refine_premesh(premesh, Nodes1D.create(order - 1, GL))
+  vhost = vref.finalize_host()
+  vmesh = dict(node_coords=vref.node_coords, elements=vref.elements,
+               interior_mask=1.0 - vhost['physical_masks']['boundary'],
+               exchange_gather_indices=vhost['exchange_gather_indices'],
+               exchange_unique_indices=vhost['exchange_unique_indices'])
+  pmesh = dict(node_coords=pref.node_coords, elements=pref.elements)
+  return vmesh, pmesh
+
+
+def stokes_reference_soln_params(k=1., viscosity=1.):
+  """navier_stokes_test.py:47-54."""
+  import scipy.optimize  # pylint: disable=g-import-not-at-top
+  mu = scipy.optimize.newton(lambda x: k * np.tanh(k) + x * np.tan(x), np.pi)
+  return mu, -viscosity * (np.square(k) + np.square(mu))
+
+
+def stokes_reference_soln(vcoords, pcoords, t, k=1., viscosity=1.):
+  """Analytical Stokes vortices (navier_stokes_test.py:57-68)."""
+  mu, sigma = stokes_reference_soln_params(k, viscosity)
+  f = lambda x: np.cos(mu) * np.cosh(k * x) - np.cosh(k) * np.cos(mu * x)  # noqa: E731
+  g = lambda x: (1j / k) * (k * np.cos(mu) * np.sinh(k * x) +  # noqa: E731
+                            mu * np.cosh(k) * np.sin(mu * x))
+  h = lambda x: -(sigma / k) * np.cos(mu) * np.sinh(k * x)  # noqa: E731
+  lead = lambda x: np.exp(sigma * t) * np.exp(1j * k * x[:, 1])  # noqa: E731
+  u = np.real(lead(vcoords)[:, None] * np.stack(
+      [f(vcoords[:, 0]), g(vcoords[:, 0])], -1))
+  p = np.real(lead(pcoords) * h(pcoords[:, 0]))
+  return u, p
