@@ -205,17 +205,41 @@ def test_fespace_matches_reference(name, dtype):
                float(g[p + 'integral_div'])) < tol * 10
 
 
-def test_local_covector_rejects_unsupported_forms():
+def test_local_covector_general_forms_and_errors():
+  """Forms outside the Helmholtz family take the general path (evaluation +
+  transposed evaluation kernels = the reference's linear_transpose,
+  fespace.py:458-471); compared with the dense oracle."""
+  from oracle import dense_ns
   from swirl_fem_b200.core import fespace as fs
   g = load_golden('operator')
-  mesh, space = _space_from_golden(g, 'q2_ne2_p3_gl4/', torch.float64)
-  uf = space.scalar_function(mesh.gather(dev(g['q2_ne2_p3_gl4/u'])))
+  p = 'q2_ne2_p3_gl4/'
+  mesh, space = _space_from_golden(g, p, torch.float64)
+  ndim, _, n, qt, q = [int(v) for v in g[p + 'meta']]
+  oracle = dense.FESpace(g[p + 'node_coords'], g[p + 'elements'], n,
+                         helpers.TNAME[GLL], q,
+                         helpers.TNAME[GL if qt == 1 else GLL])
+  u_local = oracle.gather(g[p + 'u'])
+  uq = oracle.eval_scalar(u_local)
+  uf = space.scalar_function(mesh.gather(dev(g[p + 'u'])))
   vf = space.scalar_function(None)
-  with pytest.raises(NotImplementedError):
-    space.local_covector(lambda u, v: (lambda x: u(x) * fs.grad(v)(x)[0]),
-                         (uf, vf))
-  with pytest.raises(NotImplementedError):
-    space.local_covector(lambda u, v: (lambda x: x[0] * u(x) * v(x)), (uf, vf))
+  # u * d v / d x_0
+  got = space.local_covector(
+      lambda u, v: (lambda x: u(x) * fs.grad(v)(x)[0]), (uf, vf))
+  coeff = np.zeros(uq.shape + (ndim,))
+  coeff[..., 0] = uq
+  assert rel_err(got.cpu(), dense_ns.covector(oracle, grads=coeff)) < 1e-12
+  # x_0 * u * v (variable coefficient)
+  got = space.local_covector(lambda u, v: (lambda x: x[0] * u(x) * v(x)),
+                             (uf, vf))
+  want = dense_ns.covector(oracle, vals=oracle.quad_coords[..., 0] * uq)
+  assert rel_err(got.cpu(), want) < 1e-12
+  # linear form with an analytic data function: f(x) v
+  got = space.local_covector(
+      lambda f, v: (lambda x: f(x) * v(x)),
+      (lambda x: 1 + 5 * x[0] - x[1] ** 2, vf))
+  xq = oracle.quad_coords
+  want = dense_ns.covector(oracle, vals=1 + 5 * xq[..., 0] - xq[..., 1] ** 2)
+  assert rel_err(got.cpu(), want) < 1e-12
   with pytest.raises(ValueError):
     space.local_covector(lambda u, v: (lambda x: u(x) * v(x)), (uf, uf))
   with pytest.raises(ValueError, match='shape'):
