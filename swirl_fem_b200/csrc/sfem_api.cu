@@ -129,14 +129,27 @@ int op_apply_internal(const sfem_op* op, double lambda, double mu,
                "operator was created without mass factors (with_mass = 0) but "
                "lambda != 0");
   const size_t esz = d.dtype == SFEM_F64 ? 8 : 4;
-  if (op->n_zero > 0)
-    SFEM_CUDA_CHECK(cudaMemsetAsync(y, 0, esz * (size_t)op->n_zero * ncomp,
-                                    stream));
-  if (dot_xy) SFEM_CUDA_CHECK(cudaMemsetAsync(dot_xy, 0, sizeof(double), stream));
+  // 3-D collocated kernels: zero fill by our own kernel, apply launched as its
+  // programmatic dependent (prologue overlaps the fill)
+  const bool pdl = op->variant == 0 && d.collocated && d.dim == 3 &&
+                   d.n1d <= 16 && (op->n_zero > 0 || dot_xy);
+  sfem_op sub = *op;
+  sub.pdl = pdl;
+  if (pdl) {
+    int rc = launch_zero_fill(y, esz * (size_t)op->n_zero * ncomp, dot_xy,
+                              stream);
+    if (rc) return rc;
+  } else {
+    if (op->n_zero > 0)
+      SFEM_CUDA_CHECK(cudaMemsetAsync(y, 0, esz * (size_t)op->n_zero * ncomp,
+                                      stream));
+    if (dot_xy)
+      SFEM_CUDA_CHECK(cudaMemsetAsync(dot_xy, 0, sizeof(double), stream));
+  }
   return d.dtype == SFEM_F64
-             ? apply_dispatch<double>(*op, lambda, mu, x, y, ncomp, false,
+             ? apply_dispatch<double>(sub, lambda, mu, x, y, ncomp, false,
                                       dot_xy, stream)
-             : apply_dispatch<float>(*op, lambda, mu, x, y, ncomp, false,
+             : apply_dispatch<float>(sub, lambda, mu, x, y, ncomp, false,
                                      dot_xy, stream);
 }
 

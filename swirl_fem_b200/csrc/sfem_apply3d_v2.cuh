@@ -334,6 +334,11 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     hpoll = hd.flags + hd.peer_ranks[threadIdx.x];
   const bool stamp = HALO && blockIdx.x == 0 && threadIdx.x == 0;
   if (stamp) halo_stamp(hd, 0);
+  // programmatic dependent launch: whatever follows may be scheduled as this
+  // grid drains; this grid itself may have started before the zero fill of y
+  // finished (see sfem_op::pdl) and waits for it before its first write
+  pdl_launch_dependents();
+  bool first_step = true;
 
   int buf = 0;
   for (; blk < nblocks; blk += gridDim.x, buf ^= 1) {
@@ -554,6 +559,10 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     __syncthreads();
 
     // ---- phase 5 (mapping A): sum the three parts, scatter
+    if (first_step) {
+      pdl_wait();
+      first_step = false;
+    }
     if (active) {
 #pragma unroll
       for (int k = 0; k < N; ++k) {
@@ -689,9 +698,10 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
     hd = f;
     hd.n_if_blocks = (hd.n_if_blocks + C::epb - 1) / C::epb;
   }
-  kernel<<<grid, C::threads, smem, stream>>>(
-      dm, op.conn, (const T*)op.geom, (T)lambda, (T)mu, (const T*)x, (T*)y,
-      ncomp, E, dot_xy, hd);
+  SFEM_CUDA_CHECK(launch_maybe_pdl(
+      op.pdl, kernel, grid, dim3(C::threads), smem, stream, dm, op.conn,
+      (const T*)op.geom, (T)lambda, (T)mu, (const T*)x, (T*)y, ncomp, E,
+      dot_xy, hd));
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }

@@ -344,4 +344,39 @@ struct sfem_op {
   // apply kernel (interface elements first).  The launcher sizes the work
   // items for its grid (fields slice / uslice / num_slices / num_uslices).
   sfem::HaloDev* fuse = nullptr;
+  // set on a shallow copy: the preceding stream operation is zero_fill_kernel,
+  // launch the apply with programmatic dependent launch (its prologue --
+  // connectivity, gather, first bulk copy -- overlaps the zero fill; it waits
+  // with griddepcontrol.wait before its first write to y)
+  bool pdl = false;
 };
+
+namespace sfem {
+// Zero fill of y's shared-dof prefix and of the dot accumulator by ONE small
+// kernel (one CTA per SM) that lets its dependents launch at once.
+int launch_zero_fill(void* y, size_t bytes, double* dot_xy, cudaStream_t stream);
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic stream
+// serialization attribute when `pdl`.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_maybe_pdl(bool pdl, void (*kernel)(KArgs...),
+                                    dim3 grid, dim3 block, size_t smem,
+                                    cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;");
+}
+}  // namespace sfem

@@ -192,6 +192,21 @@ unpack_canonical_kernel(T* __restrict__ u, const int32_t* __restrict__ dofs,
   }
 }
 
+// ---- zero fill with early dependent launch -----------------------------------
+__global__ void __launch_bounds__(256)
+zero_fill_kernel(uint4* __restrict__ p16, size_t n16, unsigned char* tail,
+                 int ntail, double* dot_xy) {
+  pdl_launch_dependents();
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16;
+       i += (size_t)gridDim.x * blockDim.x)
+    p16[i] = z;
+  if (blockIdx.x == 0) {
+    if ((int)threadIdx.x < ntail) tail[threadIdx.x] = 0;
+    if (threadIdx.x == 0 && dot_xy) *dot_xy = 0.0;
+  }
+}
+
 // ---- connectivity packing -------------------------------------------------------
 __global__ void count_kernel(const int32_t* __restrict__ elements, int64_t total,
                              int32_t* __restrict__ counts) {
@@ -306,6 +321,28 @@ struct sfem_scatter_plan {
   int32_t* keys;  // sorted node ids (count)
   int32_t* perm;  // matching local slots (count)
 };
+
+namespace sfem {
+
+// y is a torch / XLA allocation (>= 256-byte aligned); the last bytes % 16 are
+// written one by one.
+int launch_zero_fill(void* y, size_t bytes, double* dot_xy,
+                     cudaStream_t stream) {
+  if (((uintptr_t)y & 15u) != 0) {  // unaligned views: plain memsets
+    if (bytes) SFEM_CUDA_CHECK(cudaMemsetAsync(y, 0, bytes, stream));
+    if (dot_xy)
+      SFEM_CUDA_CHECK(cudaMemsetAsync(dot_xy, 0, sizeof(double), stream));
+    return SFEM_OK;
+  }
+  const size_t n16 = bytes / 16;
+  zero_fill_kernel<<<num_sms(), 256, 0, stream>>>(
+      (uint4*)y, n16, (unsigned char*)y + n16 * 16, (int)(bytes - n16 * 16),
+      dot_xy);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+}  // namespace sfem
 
 extern "C" {
 

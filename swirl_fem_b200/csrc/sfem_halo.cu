@@ -59,6 +59,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 halo_wait_unpack_kernel(T* __restrict__ u, const __grid_constant__ HaloDev hd) {
   __shared__ unsigned s_slice;
+  pdl_wait();  // launched as a programmatic dependent of the apply kernel
   // other CTAs claim slices concurrently: one thread decides for the CTA
   if (threadIdx.x == 0) s_slice = ld_relaxed_gpu(&hd.counters[5]);
   __syncthreads();
@@ -279,11 +280,13 @@ int sfem_halo_wait_unpack(sfem_halo* halo, void* u, sfem_stream_t stream_) {
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   if (d.dtype == SFEM_F64)
-    halo_wait_unpack_kernel<double><<<(int)b, kThreads, 0, stream>>>((double*)u,
-                                                                     hd);
+    SFEM_CUDA_CHECK(launch_maybe_pdl(true, halo_wait_unpack_kernel<double>,
+                                     dim3((unsigned)b), dim3(kThreads), 0,
+                                     stream, (double*)u, hd));
   else
-    halo_wait_unpack_kernel<float><<<(int)b, kThreads, 0, stream>>>((float*)u,
-                                                                    hd);
+    SFEM_CUDA_CHECK(launch_maybe_pdl(true, halo_wait_unpack_kernel<float>,
+                                     dim3((unsigned)b), dim3(kThreads), 0,
+                                     stream, (float*)u, hd));
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }
@@ -334,12 +337,16 @@ int sfem_op_apply_halo(const sfem_op* op, sfem_halo* halo, double lambda,
     return sfem_halo_push(halo, y, stream_);
   }
   const size_t esz = d.dtype == SFEM_F64 ? 8 : 4;
-  if (op->n_zero > 0)
-    SFEM_CUDA_CHECK(cudaMemsetAsync(y, 0, esz * (size_t)op->n_zero, stream));
-  if (dot_xy) SFEM_CUDA_CHECK(cudaMemsetAsync(dot_xy, 0, sizeof(double), stream));
+  const bool pdl = op->n_zero > 0 || dot_xy;
+  if (pdl) {
+    int rc = launch_zero_fill(y, esz * (size_t)op->n_zero, (double*)dot_xy,
+                              stream);
+    if (rc) return rc;
+  }
   HaloDev hd = begin_epoch(halo, num_interface_elements);
   sfem_op sub = *op;
   sub.fuse = &hd;  // the launcher sizes the work items for its grid
+  sub.pdl = pdl;
   const int rc = d.dtype == SFEM_F64
                      ? launch_apply3d_halo<double>(sub, lambda, mu, x, y,
                                                    (double*)dot_xy, stream)
