@@ -133,3 +133,87 @@ def stokes_reference_soln(vcoords, pcoords, t, k=1., viscosity=1.):
       [f(vcoords[:, 0]), g(vcoords[:, 0])], -1))
   p = np.real(lead(pcoords) * h(pcoords[:, 0]))
   return u, p
+
+
+# -- Gmsh .msh writers (fixtures for the reader tests) -----------------------------
+
+_GMSH_FROM_LEX = {1: [0, 1], 2: [0, 2, 3, 1], 3: [0, 4, 6, 2, 1, 5, 7, 3]}
+_GMSH_TYPE = {'line': 1, 'quad': 3, 'hexahedron': 5}
+
+
+def write_msh41(path, points, cells, periodic=(), tag_stride=1):
+  """Minimal ASCII MSH 4.1 writer.  `cells`: name -> (n, k) 0-based node
+  indices in GMSH ordering; `periodic`: (entity_dim, (n, 2) node index pairs).
+  Node tags are `1 + tag_stride * index` (non-contiguous for stride > 1)."""
+  points = np.asarray(points, dtype=np.float64)
+  pts = np.zeros((len(points), 3))
+  pts[:, :points.shape[1]] = points
+  tag = lambda i: 1 + tag_stride * int(i)  # noqa: E731
+  out = ['$MeshFormat', '4.1 0 8', '$EndMeshFormat', '$Nodes',
+         f'1 {len(pts)} 1 {tag(len(pts) - 1)}', f'2 1 0 {len(pts)}']
+  out += [str(tag(i)) for i in range(len(pts))]
+  out += [' '.join(repr(float(v)) for v in p) for p in pts]
+  out += ['$EndNodes', '$Elements']
+  total = sum(len(v) for v in cells.values())
+  out.append(f'{len(cells)} {total} 1 {total}')
+  etag = 1
+  for k, (name, conn) in enumerate(cells.items()):
+    dim = {'line': 1, 'quad': 2, 'hexahedron': 3}[name]
+    out.append(f'{dim} {k + 1} {_GMSH_TYPE[name]} {len(conn)}')
+    for row in conn:
+      out.append(' '.join([str(etag)] + [str(tag(i)) for i in row]))
+      etag += 1
+  out.append('$EndElements')
+  if periodic:
+    out += ['$Periodic', str(len(periodic))]
+    for dim, pairs in periodic:
+      out += [f'{dim} 2 1', '16 1 0 0 0 0 1 0 0 0 0 1 0 0 0 0 1',
+              str(len(pairs))]
+      out += [f'{tag(a)} {tag(b)}' for a, b in pairs]
+    out.append('$EndPeriodic')
+  with open(path, 'w') as f:
+    f.write('\n'.join(out) + '\n')
+
+
+def write_msh22(path, points, cells, tag_stride=1):
+  points = np.asarray(points, dtype=np.float64)
+  pts = np.zeros((len(points), 3))
+  pts[:, :points.shape[1]] = points
+  tag = lambda i: 1 + tag_stride * int(i)  # noqa: E731
+  out = ['$MeshFormat', '2.2 0 8', '$EndMeshFormat', '$Nodes', str(len(pts))]
+  out += [' '.join([str(tag(i))] + [repr(float(v)) for v in p])
+          for i, p in enumerate(pts)]
+  out += ['$EndNodes', '$Elements',
+          str(sum(len(v) for v in cells.values()))]
+  etag = 1
+  for name, conn in cells.items():
+    for row in conn:
+      out.append(' '.join([str(etag), str(_GMSH_TYPE[name]), '2', '1', '1'] +
+                          [str(tag(i)) for i in row]))
+      etag += 1
+  out.append('$EndElements')
+  with open(path, 'w') as f:
+    f.write('\n'.join(out) + '\n')
+
+
+def write_premesh_as_msh(path, premesh, version='4.1', tag_stride=1):
+  """Writes a first-order `Premesh` (lexicographic cells) as a Gmsh file with
+  Gmsh's cell ordering; periodic links become facet cells + `$Periodic`."""
+  ndim = premesh.ndim
+  name = {1: 'line', 2: 'quad', 3: 'hexahedron'}[ndim]
+  cells = {name: np.asarray(premesh.elements)[:, _GMSH_FROM_LEX[ndim]]}
+  periodic = []
+  links = premesh.periodic_links
+  if links is not None and len(links):
+    links = np.asarray(links)
+    fname = {2: 'line', 3: 'quad'}[ndim]
+    # facet cells (any consistent ordering: the reader keeps it as listed)
+    cells = {fname: np.concatenate([links[:, 0], links[:, 1]]), **cells}
+    pairs = np.unique(np.stack([links[:, 0].reshape(-1),
+                                links[:, 1].reshape(-1)], axis=1), axis=0)
+    periodic = [(ndim - 1, pairs)]
+  if version.startswith('4'):
+    write_msh41(path, premesh.node_coords, cells, periodic, tag_stride)
+  else:
+    assert not periodic
+    write_msh22(path, premesh.node_coords, cells, tag_stride)
