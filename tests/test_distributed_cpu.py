@@ -229,3 +229,104 @@ def test_p2p_tables_reject_inconsistent_counts():
   from swirl_fem_b200.communication.halo import p2p_tables
   with pytest.raises(ValueError, match='disagree'):
     p2p_tables(0, [1], {1: 5}, [[0, 5], [4, 0]], {1: 1 << 20}, 8)
+
+
+# -- crystal router and prefix scan --------------------------
+
+
+def _init(rank, world, port):
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+
+
+def _crystal_worker(rank, world, port, outdir):
+  """crystal_router_test.py:36-79 with one process per axis index."""
+  from swirl_fem_b200.communication.crystal_router import crystal_router_setup
+  _init(rank, world, port)
+  try:
+    m = 7
+    rng = np.random.RandomState(seed=2)
+    num = rng.randint(low=m // 2, high=m + 1, size=(world,)).astype(np.int32)
+    target = rng.randint(low=0, high=world, size=(world, m)).astype(np.int32)
+    data = rng.randint(100, size=(world, m)).astype(np.int32)
+    mask = np.arange(m) < num[:, None]
+    in_src = np.where(mask, np.arange(world)[:, None], -1)
+    target = np.where(mask, target, 0)
+    crystal = crystal_router_setup(None)
+    n_out, out, source = crystal(int(num[rank]), torch.as_tensor(data[rank]),
+                                 torch.as_tensor(target[rank]))
+    lexsorted = lambda *a: np.array([*a])[:, np.lexsort([*a])]  # noqa: E731
+    ft, fs, fd = (target.flatten()[mask.flatten()],
+                  in_src.flatten()[mask.flatten()],
+                  data.flatten()[mask.flatten()])
+    sel = ft == rank
+    np.testing.assert_array_equal(
+        lexsorted(fd[sel], fs[sel]),
+        lexsorted(out.numpy()[:n_out], source.numpy()[:n_out]))
+    # pytree payload + no source
+    n2, out2 = crystal(int(num[rank]),
+                       {'a': torch.as_tensor(data[rank]),
+                        'b': torch.as_tensor(data[rank]).double()[:, None] * 2},
+                       torch.as_tensor(target[rank]), return_source=False)
+    assert n2 == n_out
+    np.testing.assert_array_equal(np.sort(out2['a'].numpy()),
+                                  np.sort(out.numpy()[:n_out]))
+    np.testing.assert_array_equal(out2['b'].numpy()[:, 0],
+                                  2.0 * out2['a'].numpy())
+    # second invocation restores the data up to ordering
+    pad = lambda t: torch.cat([t, t.new_zeros(world * m - len(t))])  # noqa: E731
+    n_back, back, src_back = crystal(n_out, pad(out), pad(source))
+    np.testing.assert_array_equal(
+        lexsorted(data[rank, :num[rank]], target[rank, :num[rank]]),
+        lexsorted(back.numpy()[:n_back], src_back.numpy()[:n_back]))
+    with pytest.raises(ValueError):
+      crystal(1, torch.zeros(3), torch.full((3,), world, dtype=torch.int32))
+    open(os.path.join(outdir, f'ok{rank}'), 'w').close()
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_crystal_router_semantics(world, tmp_path):
+  _run(_crystal_worker, world, str(tmp_path))
+  assert len(os.listdir(tmp_path)) == world
+
+
+def _pscan_worker(rank, world, port, outdir):
+  """pscan_test.py:60-95 with one process per axis index."""
+  from swirl_fem_b200.communication.pscan import preduce, pscan
+  _init(rank, world, port)
+  try:
+    for x in (np.arange(world), np.flip(np.arange(world)).copy()):
+      for op in ('add', 'multiply', 'maximum', 'minimum', 'bitwise_and',
+                 'bitwise_or', 'bitwise_xor'):
+        np_op = getattr(np, op)
+        mine = torch.as_tensor(x[rank:rank + 1])
+        exclusive = pscan(mine, op)
+        inclusive = np_op.accumulate(x)
+        assert np_op(exclusive.numpy()[0], x[rank]) == inclusive[rank], op
+        ex2, red = pscan(mine, op, reduction=True)
+        assert torch.equal(ex2, exclusive)
+        assert red.numpy()[0] == np_op.reduce(x)
+        assert preduce(mine, op).numpy()[0] == np_op.reduce(x)
+    # pytree, floating point, multi-entry leaves: global numbering offsets
+    tree = {'count': torch.tensor([rank + 1, 2 * rank]),
+            'w': torch.tensor([0.5 * (rank + 1)], dtype=torch.float64)}
+    scan, red = pscan(tree, torch.add, reduction=True)
+    assert scan['count'].tolist() == [rank * (rank + 1) // 2,
+                                      rank * (rank - 1)]
+    assert red['count'].tolist() == [world * (world + 1) // 2,
+                                     world * (world - 1)]
+    assert float(scan['w']) == 0.5 * rank * (rank + 1) / 2
+    with pytest.raises(ValueError):
+      pscan(torch.zeros(1), 'subtract')
+    open(os.path.join(outdir, f'ok{rank}'), 'w').close()
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_pscan_and_preduce(world, tmp_path):
+  _run(_pscan_worker, world, str(tmp_path))
+  assert len(os.listdir(tmp_path)) == world
