@@ -322,6 +322,16 @@ def run_ours(args):
     total_ms = float(t.item())
   ms_per_step = total_ms / args.steps
   value = num_global / (ms_per_step * 1e-3) / 1e9
+  # where inside the last fused launch the exchange happened (globaltimer
+  # stamps written by the kernel): evidence that it overlaps the interior
+  halo_timeline = None
+  if halo is not None and rank == 0:
+    try:
+      if halo.p2p_handle(x) is not None:
+        halo_timeline = halo.p2p_debug_times(device)
+        halo_timeline['unit'] = 'us from the start of the apply kernel (rank 0)'
+    except Exception as e:  # diagnostics only  pylint: disable=broad-except
+      halo_timeline = {'error': str(e)}
 
   # roofline of the dominant kernel: per-rank algorithmic bytes / apply time
   # (the un-fused kernel instance has not run yet when the step is the
@@ -458,6 +468,7 @@ def run_ours(args):
             'workload': config_name(args),
             'partition': 'x'.join(str(g) for g in blk.grid),
             'halo_exchange': halo_path,
+            'halo_timeline': halo_timeline,
             'local_dofs_rank0': mesh.num_nodes,
             'elements_rank0': mesh.num_elements,
             'l2_policy': 'inputs larger than L2 (geometric factors '

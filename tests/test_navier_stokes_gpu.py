@@ -236,3 +236,55 @@ def test_stokes_one_step_analytical_and_oracle(vortices):
                    auxo[key]['num_iterations'])
   assert np.abs(u.cpu().numpy() - uo).max() < 1e-9
   assert np.abs(p.cpu().numpy() - po).max() < 1e-6
+
+
+def test_gmsh_file_drives_the_stokes_operators(tmp_path):
+  """a `.msh` file (Gmsh cell ordering, $Periodic section)
+  read by `common.mesh_reader` feeds the same operators as the generated
+  premesh it was written from."""
+  from swirl_fem_b200.common import mesh_reader
+  pm0 = helpers.stokes_vortices_premesh(3, curved=0.1)
+  path = tmp_path / 'vortices.msh'
+  helpers.write_premesh_as_msh(path, pm0, version='4.1', tag_stride=2)
+  pm = mesh_reader.read(path, ndim=2)
+  # the reader does not carry physical groups (mesh_reader.py:108-114): take
+  # the boundary facets from the generator
+  pm = pm.replace(physical_groups=pm0.physical_groups)
+  np.testing.assert_array_equal(pm.elements, pm0.elements)
+  sem = _sem(pm, 4)
+  vmesh, pmesh = helpers.stokes_oracle_meshes(pm0, 4)
+  osem = dense_ns.StokesSEM(vmesh, pmesh, 4)
+  rng = np.random.default_rng(11)
+  u = rng.standard_normal((vmesh['node_coords'].shape[0], 2))
+  p = rng.standard_normal(pmesh['node_coords'].shape[0])
+  assert rel_err(sem.A(dev(u)), osem.A(u)) < 1e-12
+  assert rel_err(sem.D(dev(u)), osem.D(u)) < 1e-12
+  assert rel_err(sem.Dt(dev(p)), osem.Dt(p)) < 1e-12
+  assert rel_err(sem.velocity.exchange(dev(u)), osem.v_exchange(u)) < 1e-14
+
+
+def test_differentiable_solve_symmetric():
+  """`custom_linear_solve(symmetric=True)` -- the
+  cotangent of b is one more CG solve with the same operator
+  (navier_stokes.py:436-452)."""
+  from swirl_fem_b200.linalg.cg import cg
+  from swirl_fem_b200.linalg.differentiable import custom_linear_solve
+  pm = helpers.stokes_vortices_premesh(3, curved=0.1)
+  sem = _sem(pm, 4)
+  dt, beta_k = 1e-2, 11.0 / 6.0
+  H_ = lambda v: (beta_k / dt) * sem.B(v) + sem.A(v)  # noqa: E731
+  solve = lambda mv, rhs: cg(mv, rhs, M=sem.velocity.exchange, tol=1e-13)  # noqa: E731
+  rng = np.random.default_rng(5)
+  n = sem.velocity.mesh.num_nodes
+  mask = sem.velocity.interior_mask
+  b = (dev(rng.standard_normal((n, 2))) * mask).requires_grad_(True)
+  w = dev(rng.standard_normal((n, 2))) * mask
+  x, aux = custom_linear_solve(H_, b, solve, symmetric=True, has_aux=True)
+  assert aux['num_iterations'] > 0
+  loss = (w * x).sum()
+  loss.backward()
+  # d/db <w, H^-1 b> = H^-T w = H^-1 w
+  want, _ = solve(H_, w)
+  assert rel_err(b.grad, want.cpu().numpy()) < 1e-9
+  with pytest.raises(ValueError, match='transpose_solve'):
+    custom_linear_solve(H_, b, solve)
