@@ -101,4 +101,54 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(sfem_xla_op_apply_local, OpApplyLocalImpl,
                                   .Attr<double>("lam")
                                   .Attr<double>("mu"));
 
+// Partitioned A(u): local operator + the psum of gather_scatter.exchange
+// (swirl_fem/core/gather_scatter.py:246-248) as ONE launch with the in-kernel
+// peer-memory push, then the wait + canonical sum.  `op` / `halo` = addresses
+// of the sfem_op / sfem_halo created once outside jit.
+static ffi::Error OpApplyHaloImpl(cudaStream_t stream, ffi::AnyBuffer x,
+                                  ffi::Result<ffi::AnyBuffer> y, int64_t op,
+                                  int64_t halo, int64_t num_interface_elements,
+                                  double lam, double mu) {
+  int rc = sfem_op_apply_halo(reinterpret_cast<const sfem_op*>(op),
+                              reinterpret_cast<sfem_halo*>(halo), lam, mu,
+                              x.untyped_data(), y->untyped_data(),
+                              num_interface_elements, nullptr,
+                              (sfem_stream_t)stream);
+  if (rc == SFEM_OK)
+    rc = sfem_halo_wait_unpack(reinterpret_cast<sfem_halo*>(halo),
+                               y->untyped_data(), (sfem_stream_t)stream);
+  return Status(rc);
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(sfem_xla_op_apply_halo, OpApplyHaloImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<int64_t>("op")
+                                  .Attr<int64_t>("halo")
+                                  .Attr<int64_t>("num_interface_elements")
+                                  .Attr<double>("lam")
+                                  .Attr<double>("mu"));
+
+// Transposed evaluation = jax.linear_transpose of the quadrature integral
+// (swirl_fem/core/fespace.py:458-471) for a form linear in its placeholder:
+// vals (E, q, c) / grads (E, q, d, c) -> covector (E, n, c).
+static ffi::Error EvalTransposeImpl(cudaStream_t stream, ffi::AnyBuffer vals,
+                                    ffi::AnyBuffer grads,
+                                    ffi::Result<ffi::AnyBuffer> out,
+                                    int64_t space, int64_t ncomp) {
+  return Status(sfem_space_eval_transpose(
+      reinterpret_cast<const sfem_space*>(space), vals.untyped_data(),
+      grads.untyped_data(), (int32_t)ncomp, out->untyped_data(),
+      (sfem_stream_t)stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(sfem_xla_space_eval_transpose, EvalTransposeImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<int64_t>("space")
+                                  .Attr<int64_t>("ncomp"));
+
 #endif  // __has_include("xla/ffi/api/ffi.h")
