@@ -166,6 +166,17 @@ int sfem_space_eval_transpose(const sfem_space* space, const void* vals,
                               const void* grads, int32_t ncomp, void* out,
                               sfem_stream_t stream);
 
+/* Pointwise forms of the Stokes operators at the quadrature points, between
+ * sfem_space_eval and sfem_space_eval_transpose (AoS layouts of those calls):
+ *   kind 0: out[p] = sum_k g[p][k][k]              div(v), navier_stokes.py:315
+ *   kind 1: out[p][j][k] = (j == k) a[p]           coefficient of grad v in
+ *                                                  div(v) q, navier_stokes.py:324
+ *   kind 2: out[p][k] = sum_i a[p][i] g[p][i][k]   (u . grad) w, :239-240
+ * a: (P) [kind 1] or (P, d) [kind 2]; g: (P, d, d) with g[j][k] = d w_k / d x_j. */
+int sfem_pointwise(int dtype, int32_t kind, int32_t dim, const void* a,
+                   const void* g, int64_t num_points, void* out,
+                   sfem_stream_t stream);
+
 /* FiniteElementSpace.integrate (fespace.py:381-403):
  * *result = sum_{e,q} w[e,q] * jacdets[e,q] * W[q].  result: device fp64
  * scalar (always double, zeroed by the call). */

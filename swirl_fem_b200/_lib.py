@@ -118,6 +118,8 @@ SIGNATURES = {
                                        _c_ptr]),
     'sfem_space_eval_transpose': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr,
                                                  _c_i32, _c_ptr, _c_ptr]),
+    'sfem_pointwise': (ctypes.c_int, [ctypes.c_int, _c_i32, _c_i32, _c_ptr,
+                                      _c_ptr, _c_i64, _c_ptr, _c_ptr]),
     'sfem_space_integrate': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr]),
     'sfem_op_geom_bytes': (_c_i64, [ctypes.POINTER(SpaceDesc), _c_i32]),
     'sfem_op_conn_bytes': (_c_i64, [ctypes.POINTER(SpaceDesc)]),
@@ -319,6 +321,17 @@ def exchange(u: torch.Tensor, gather_indices: torch.Tensor,
     _check(lib().sfem_exchange(dtype_code(u.dtype), ptr(out), ptr(gi), ptr(ui),
                                count, num_unique, 1, 0, ptr(scratch),
                                stream_ptr(u.device)), 'sfem_exchange')
+  return out
+
+
+def pointwise(kind: int, dim: int, a, g, out):
+  """`sfem_pointwise`: trace (0), scalar times identity (1), convection (2)."""
+  require_cuda(a, g, out)
+  npts = out.numel() // {0: 1, 1: dim * dim, 2: dim}[kind]
+  with torch.cuda.device(out.device):
+    _check(lib().sfem_pointwise(dtype_code(out.dtype), kind, dim, ptr(a),
+                                ptr(g), npts, ptr(out),
+                                stream_ptr(out.device)), 'sfem_pointwise')
   return out
 
 

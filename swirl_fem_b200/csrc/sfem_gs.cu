@@ -192,6 +192,36 @@ unpack_canonical_kernel(T* __restrict__ u, const int32_t* __restrict__ dofs,
   }
 }
 
+// ---- pointwise forms of the Stokes operators at the quadrature points ---------
+// (navier_stokes.py:238-245, 313-329; AoS layouts of sfem_space_eval)
+//   kind 0  trace:    out[p]       = sum_k g[p][k][k]           (div v)
+//   kind 1  diagonal: out[p][j][k] = (j == k) a[p]              (q I, coefficient
+//                                                                of grad v in div(v) q)
+//   kind 2  convect:  out[p][k]    = sum_i a[p][i] g[p][i][k]   ((u . grad) w)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+pointwise_kernel(int kind, int d, const T* __restrict__ a,
+                 const T* __restrict__ g, int64_t npts, T* __restrict__ out) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npts;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    if (kind == 0) {
+      T acc = T(0);
+      for (int k = 0; k < d; ++k) acc += g[(p * d + k) * d + k];
+      out[p] = acc;
+    } else if (kind == 1) {
+      const T v = a[p];
+      for (int j = 0; j < d; ++j)
+        for (int k = 0; k < d; ++k) out[(p * d + j) * d + k] = j == k ? v : T(0);
+    } else {
+      for (int k = 0; k < d; ++k) {
+        T acc = T(0);
+        for (int i = 0; i < d; ++i) acc += a[p * d + i] * g[(p * d + i) * d + k];
+        out[p * d + k] = acc;
+      }
+    }
+  }
+}
+
 // ---- zero fill with early dependent launch -----------------------------------
 __global__ void __launch_bounds__(256)
 zero_fill_kernel(uint4* __restrict__ p16, size_t n16, unsigned char* tail,
@@ -345,6 +375,28 @@ int launch_zero_fill(void* y, size_t bytes, double* dot_xy,
 }  // namespace sfem
 
 extern "C" {
+
+int sfem_pointwise(int dtype, int32_t kind, int32_t dim, const void* a,
+                   const void* g, int64_t num_points, void* out,
+                   sfem_stream_t stream_) {
+  using namespace sfem;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SFEM_REQUIRE(kind >= 0 && kind <= 2, "kind must be 0, 1 or 2");
+  SFEM_REQUIRE(dim >= 1 && dim <= 3, "dim must be 1, 2 or 3");
+  SFEM_REQUIRE(out && (kind == 1 ? a != nullptr : g != nullptr) &&
+                   (kind != 2 || a != nullptr),
+               "null argument");
+  if (num_points == 0) return SFEM_OK;
+  if (dtype == SFEM_F64)
+    pointwise_kernel<double><<<blocks_for(num_points), kThreads, 0, stream>>>(
+        kind, dim, (const double*)a, (const double*)g, num_points,
+        (double*)out);
+  else
+    pointwise_kernel<float><<<blocks_for(num_points), kThreads, 0, stream>>>(
+        kind, dim, (const float*)a, (const float*)g, num_points, (float*)out);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
 
 int sfem_gather(int dtype, const void* u, const int32_t* indices, int64_t count,
                 double fill_value, int32_t stride, int32_t offset, void* out,

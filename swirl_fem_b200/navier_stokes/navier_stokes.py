@@ -214,7 +214,21 @@ class StokesVelocity:
     return self.vspace.local_covector(l, (u, v))
 
   def C_local(self, u_local):
-    """Apply the local convection operator: u_i d_i w_j v_j."""
+    """Apply the local convection operator: u_i d_i w_j v_j.
+
+    Fixed form -> three kernels (values and gradients on the over-integration
+    rule, `(u . grad) u` pointwise, transposed evaluation);
+    `C_local_general` keeps the reference's form-based formulation."""
+    sp = self.overint_space
+    d = sp.mesh.ndim
+    u_local = u_local.to(sp.dtype).contiguous()
+    uq = sp._eval(u_local, ncomp=d, kind=0)    # (E, q, d)
+    gq = sp._eval(u_local, ncomp=d, kind=1)    # (E, q, d, d)
+    cq = _lib.pointwise(2, d, uq, gq, torch.empty_like(uq))
+    return sp._eval_transpose(cq, None, d)
+
+  def C_local_general(self, u_local):
+    """`C_local` through `local_covector` (navier_stokes.py:238-245)."""
     def c(u, w, v):
       def f(x):
         ux, gw, vx = u(x), grad(w)(x), v(x)
@@ -288,7 +302,30 @@ class StokesSEM:
     return self.velocity.C(u)
 
   def D_local(self, u_local):
-    """Apply the local operator D."""
+    """Apply the local operator D: div(v) tested with the pressure basis.
+
+    Fixed form -> three kernels (velocity gradient at the shared GLL points,
+    trace, transposed evaluation on the pressure space); `D_local_general`
+    keeps the reference's form-based formulation."""
+    vs, ps = self.velocity.vspace, self.pressure.pspace
+    d = vs.mesh.ndim
+    gq = vs._eval(u_local.to(vs.dtype).contiguous(), ncomp=d, kind=1)
+    div = _lib.pointwise(0, d, None, gq, torch.empty(
+        gq.shape[:2], dtype=gq.dtype, device=gq.device))
+    return ps._eval_transpose(div, None, 1)
+
+  def Dt_local(self, p_local):
+    """Apply the local operator D^T (pressure values times the velocity test
+    functions' divergence); see `D_local`."""
+    vs, ps = self.velocity.vspace, self.pressure.pspace
+    d = vs.mesh.ndim
+    pq = ps._eval(p_local.to(ps.dtype).contiguous(), ncomp=1, kind=0)
+    coeff = _lib.pointwise(1, d, pq, None, torch.empty(
+        tuple(pq.shape) + (d, d), dtype=pq.dtype, device=pq.device))
+    return vs._eval_transpose(None, coeff, d)
+
+  def D_local_general(self, u_local):
+    """`D_local` through `local_covector` (navier_stokes.py:313-320)."""
     def b(v, q):
       return lambda x: div(v)(x) * q(x)
 
@@ -296,8 +333,8 @@ class StokesSEM:
     p = self.pressure.pspace.scalar_function(None)
     return self.pressure.pspace.local_covector(b, (v, p))
 
-  def Dt_local(self, p_local):
-    """Apply the local operator D^T."""
+  def Dt_local_general(self, p_local):
+    """`Dt_local` through `local_covector` (navier_stokes.py:322-329)."""
     def b(v, q):
       return lambda x: div(v)(x) * q(x)
 

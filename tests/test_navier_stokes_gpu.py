@@ -288,3 +288,22 @@ def test_differentiable_solve_symmetric():
   assert rel_err(b.grad, want.cpu().numpy()) < 1e-9
   with pytest.raises(ValueError, match='transpose_solve'):
     custom_linear_solve(H_, b, solve)
+
+
+def test_fixed_form_kernels_equal_the_general_form_path():
+  """`D`, `D^T`, `C` run as evaluation -> `sfem_pointwise` -> transposed
+  evaluation; the reference's form-based formulation through the general
+  `local_covector` (navier_stokes.py:238-245, 313-329) gives the same."""
+  pm = helpers.stokes_vortices_premesh(3, curved=0.12)
+  sem = _sem(pm, 5)
+  rng = np.random.default_rng(1)
+  n = sem.velocity.mesh.num_nodes
+  ul = sem.velocity.gather(dev(rng.standard_normal((n, 2))))
+  pl = sem.pressure.gather(dev(rng.standard_normal(
+      sem.pressure.pspace.mesh.num_nodes)))
+  for fast, general in ((sem.D_local(ul), sem.D_local_general(ul)),
+                        (sem.Dt_local(pl), sem.Dt_local_general(pl)),
+                        (sem.velocity.C_local(ul),
+                         sem.velocity.C_local_general(ul))):
+    assert fast.shape == general.shape
+    assert rel_err(fast, general.cpu().numpy()) < 1e-13
