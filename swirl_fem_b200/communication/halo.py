@@ -279,6 +279,14 @@ class HaloPlan:
     flags = [None] * self.world
     dist.all_gather_object(flags, ok, group=group)
     if not all(flags):
+      # some rank could not export / map: release what this rank holds and
+      # keep the NCCL path everywhere
+      with torch.cuda.device(device):
+        for addr in bases.values():
+          lib.sfem_ipc_close(addr)
+        dist.barrier(group=group)
+        if region.value:
+          lib.sfem_ipc_free(region.value)
       return False
     if self.peers:
       self._p2p_attach(dtype, device, region.value, bases, all_splits)

@@ -330,3 +330,50 @@ def _pscan_worker(rank, world, port, outdir):
 def test_pscan_and_preduce(world, tmp_path):
   _run(_pscan_worker, world, str(tmp_path))
   assert len(os.listdir(tmp_path)) == world
+
+
+# -- general (non-block) partitions: partitioner -> index builders -> halo plan ----
+
+
+def _worker_general_partition(rank, world, port, seed):
+  """An 'unstructured' quad mesh (shuffled elements, rotated vertex listings)
+  partitioned by `common.mesh_partitioner`, localised by the reference's index
+  builders (`Premesh.partition_host`: group_by_partitions / get_local_elements,
+  gather_scatter.py:355-445) and exchanged with the pairwise halo plan: the
+  result equals the unpartitioned QQ^T semantics (every copy of a global dof
+  holds the sum over all copies)."""
+  from swirl_fem_b200.common import mesh_partitioner
+  from swirl_fem_b200.core.mesh_refiner import refine_premesh
+  from tests import helpers
+  _init(rank, world, port)
+  try:
+    pm = helpers.shuffled(helpers.unit_cube_mesh(6, ndim=2, a=-1., b=1.), seed)
+    pm = mesh_partitioner.partition(pm, world)
+    refined = refine_premesh(pm, Nodes1D.create(4, GLL))
+    host = refined.partition_host()
+    nidx = host['node_indices']                      # (P, n_max) global ids
+    base = HaloPlan.from_node_indices(nidx, rank)
+    plan = CpuHaloPlan(**{f: getattr(base, f) for f in
+                          ('rank', 'world', 'peers', 'local_idx', 'owned')})
+    mine = nidx[rank][nidx[rank] != -1]
+    rng = np.random.default_rng(100 + rank)
+    u = rng.standard_normal(len(mine))
+    out = plan.exchange(torch.tensor(u, dtype=torch.float64)).numpy()
+    # oracle: scatter every rank's values to the global numbering and sum
+    everyone = [None] * world
+    dist.all_gather_object(everyone, (mine, u))
+    total = np.zeros(refined.num_nodes)
+    for ids, vals in everyone:
+      np.add.at(total, ids, vals)
+    np.testing.assert_allclose(out, total[mine], rtol=1e-13, atol=1e-13)
+    # ownership weights count every global dof once
+    count = torch.tensor([float(plan.owned.sum())], dtype=torch.float64)
+    dist.all_reduce(count)
+    assert int(count.item()) == refined.num_nodes
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,seed', [(2, 3), (4, 8), (3, 5)])
+def test_general_partition_halo(world, seed):
+  _run(_worker_general_partition, world, seed)
