@@ -418,6 +418,13 @@ def run_ours(args):
       halo.exchange_(diag)
     minv_t = torch.where(diag != 0, 1.0 / diag, torch.zeros_like(diag))
 
+    # SFEM_CG_SCALARS=p2p: all-reduce the two dot products per iteration over
+    # peer memory (one single-CTA kernel each) instead of NCCL
+    sx = None
+    if world > 1 and os.environ.get('SFEM_CG_SCALARS', 'nccl') == 'p2p':
+      from swirl_fem_b200.communication.scalar_exchange import ScalarExchange
+      sx = ScalarExchange.create(device)
+
     def solve(iters):
       if world == 1:
         return cg(op.bind(0.0, 1.0), rhs, tol=0.0, maxiter=iters,
@@ -425,7 +432,8 @@ def run_ours(args):
       return distributed_cg(
           op, halo, rhs, tol=0.0, maxiter=iters, minv=minv_t,
           check_every=iters,
-          num_interface_elements=blk.num_interface_elements)
+          num_interface_elements=blk.num_interface_elements,
+          scalar_exchange=sx)
 
     solve(3)  # warm-up
     barrier()
@@ -446,7 +454,9 @@ def run_ours(args):
                'preconditioner': 'jacobi',
                'roofline_frac': cg_bytes / (cg_ms * 1e-3) / 1e9 / peak,
                'driver': 'sfem_cg (fused, 1 GPU)' if world == 1 else
-                         'distributed_cg (fused kernels + NCCL)'}
+                         ('distributed_cg (fused kernels, scalars over peer '
+                          'memory)' if sx is not None else
+                          'distributed_cg (fused kernels + NCCL scalars)')}
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -337,6 +337,27 @@ int sfem_halo_timed_out(const sfem_halo* halo, sfem_stream_t stream);
 int sfem_halo_debug_times(const sfem_halo* halo, uint64_t* out8,
                           sfem_stream_t stream);
 
+/* Peer-memory all-reduce of up to 4 doubles (the dot products of CG, whose
+ * hook in the reference is `dot_fn`, swirl_fem/linalg/cg.py:26-31): every
+ * rank owns an IPC region of sfem_scalar_region_bytes(world) zeroed bytes;
+ * `peer_regions` (HOST, world entries) holds every rank's region as mapped in
+ * this process ([rank] = my_region).  sfem_scalar_allreduce replaces
+ * values[0..count) by their sums over all ranks, added in ascending rank
+ * order (bitwise identical everywhere): ONE single-CTA kernel that stores
+ * into the peers' regions, waits on the device for theirs and adds; no NCCL
+ * launch, no host synchronisation.  Collective: same call sequence on every
+ * rank. */
+typedef struct sfem_scalar_exchange sfem_scalar_exchange;
+int64_t sfem_scalar_region_bytes(int32_t world);
+int sfem_scalar_exchange_create(int32_t rank, int32_t world, void* my_region,
+                                const uint64_t* peer_regions,
+                                sfem_scalar_exchange** out);
+void sfem_scalar_exchange_destroy(sfem_scalar_exchange* h);
+int sfem_scalar_allreduce(sfem_scalar_exchange* h, double* values,
+                          int32_t count, sfem_stream_t stream);
+int sfem_scalar_exchange_timed_out(const sfem_scalar_exchange* h,
+                                   sfem_stream_t stream);
+
 /* ------------------------------------------------------------------------ */
 /* CG (swirl_fem/linalg/cg.py:30-97)                                         */
 /* ------------------------------------------------------------------------ */

@@ -107,6 +107,13 @@ SIGNATURES = {
     'sfem_halo_wait_unpack': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr]),
     'sfem_halo_timed_out': (ctypes.c_int, [_c_ptr, _c_ptr]),
     'sfem_halo_debug_times': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr]),
+    'sfem_scalar_region_bytes': (_c_i64, [_c_i32]),
+    'sfem_scalar_exchange_create': (ctypes.c_int, [_c_i32, _c_i32, _c_ptr,
+                                                   _c_ptr,
+                                                   ctypes.POINTER(_c_ptr)]),
+    'sfem_scalar_exchange_destroy': (None, [_c_ptr]),
+    'sfem_scalar_allreduce': (ctypes.c_int, [_c_ptr, _c_ptr, _c_i32, _c_ptr]),
+    'sfem_scalar_exchange_timed_out': (ctypes.c_int, [_c_ptr, _c_ptr]),
     'sfem_op_apply_halo': (ctypes.c_int, [_c_ptr, _c_ptr, _c_f64, _c_f64,
                                           _c_ptr, _c_ptr, _c_i64, _c_ptr,
                                           _c_ptr]),

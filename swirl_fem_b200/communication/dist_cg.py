@@ -31,7 +31,7 @@ from swirl_fem_b200 import _lib
 
 def distributed_cg(op, halo, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None,
                    minv=None, lam=0.0, mu=1.0, check_every=16, group=None,
-                   num_interface_elements=None):
+                   num_interface_elements=None, scalar_exchange=None):
   """Solves `A x = b` on an element-partitioned mesh.
 
   Args:
@@ -42,6 +42,10 @@ def distributed_cg(op, halo, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None,
     minv: inverse diagonal of the *assembled* operator (exchange the local
       diagonal before inverting), or None.
     maxiter: default 10 * (global number of dofs).
+    scalar_exchange: a `communication.scalar_exchange.ScalarExchange`: the two
+      dot products per iteration are all-reduced over peer memory by one
+      single-CTA kernel each instead of an NCCL call (sums in rank order,
+      bitwise identical on all ranks).  None: NCCL.
   Returns:
     `(x, {'residual', 'num_iterations'})` as `linalg.cg.cg`.
   """
@@ -86,7 +90,10 @@ def distributed_cg(op, halo, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None,
 
   def allreduce(view):
     if world > 1:
-      dist.all_reduce(view, group=group)
+      if scalar_exchange is not None:
+        scalar_exchange.allreduce_(view)
+      else:
+        dist.all_reduce(view, group=group)
 
   with torch.cuda.device(dev):
     apply(x, None)

@@ -30,7 +30,76 @@ struct sfem_halo {
   int fuse_unpack = 1;
 };
 
+// Peer-memory all-reduce of a few doubles (the CG scalars).  Region of a rank:
+// [parity 2][source rank `world`] slots of 64 bytes {double v[4]; uint64 epoch}.
+struct sfem_scalar_exchange {
+  int rank = 0, world = 0;
+  char* my_region = nullptr;
+  uint64_t* d_peer_regions = nullptr;  // device (world) addresses
+  unsigned* d_timeout = nullptr;
+  uint64_t epoch = 0;
+};
+
 namespace sfem {
+
+namespace {
+
+struct ScalarSlot {
+  double v[4];
+  uint64_t epoch;
+  uint64_t pad[3];
+};
+static_assert(sizeof(ScalarSlot) == 64, "slot size");
+
+// ONE CTA.  Thread t publishes this rank's values into rank t's region (slot
+// of this rank) and raises the epoch there; then thread t waits for rank t's
+// epoch in the local region; thread k sums value k over the ranks in
+// ascending rank order -> bitwise identical results on every rank.
+__global__ void __launch_bounds__(128)
+scalar_allreduce_kernel(double* __restrict__ values, int count, int rank,
+                        int world, char* my_region,
+                        const uint64_t* __restrict__ peer_regions,
+                        uint64_t epoch, unsigned* timed_out) {
+  pdl_wait();
+  const unsigned parity = (unsigned)(epoch & 1u);
+  __shared__ double mine[4];
+  if ((int)threadIdx.x < count) mine[threadIdx.x] = values[threadIdx.x];
+  __syncthreads();
+  for (int t = threadIdx.x; t < world; t += blockDim.x) {
+    ScalarSlot* dst = reinterpret_cast<ScalarSlot*>(peer_regions[t]) +
+                      (parity * world + rank);
+    for (int k = 0; k < count; ++k) dst->v[k] = mine[k];
+    __threadfence_system();
+    st_release_sys(&dst->epoch, epoch);
+  }
+  for (int t = threadIdx.x; t < world; t += blockDim.x) {
+    const ScalarSlot* src =
+        reinterpret_cast<const ScalarSlot*>(my_region) + (parity * world + t);
+    uint64_t t0 = 0;
+    unsigned spins = 0;
+    while (ld_acquire_sys(&src->epoch) < epoch) {
+      if ((++spins & 1023u) == 0) {
+        uint64_t now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 4000000000ull) {
+          atomicExch(timed_out, 1u);
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < count) {
+    const ScalarSlot* base =
+        reinterpret_cast<const ScalarSlot*>(my_region) + parity * world;
+    double acc = 0.0;
+    for (int t = 0; t < world; ++t) acc += __ldcg(&base[t].v[threadIdx.x]);
+    values[threadIdx.x] = acc;
+  }
+}
+
+}  // namespace
 
 template <typename T>
 int launch_apply3d_halo(const sfem_op& op, double lambda, double mu,
@@ -193,6 +262,73 @@ int sfem_ipc_free(void* dev_ptr) {
   using namespace sfem;
   if (dev_ptr) SFEM_CUDA_CHECK(cudaFree(dev_ptr));
   return SFEM_OK;
+}
+
+int64_t sfem_scalar_region_bytes(int32_t world) {
+  return world > 0 ? (int64_t)2 * world * 64 : -1;
+}
+
+int sfem_scalar_exchange_create(int32_t rank, int32_t world, void* my_region,
+                                const uint64_t* peer_regions,
+                                sfem_scalar_exchange** out) {
+  using namespace sfem;
+  SFEM_REQUIRE(out && my_region && peer_regions, "null argument");
+  SFEM_REQUIRE(world >= 1 && world <= 128 && rank >= 0 && rank < world,
+               "bad rank / world");
+  SFEM_REQUIRE(peer_regions[rank] == (uint64_t)(uintptr_t)my_region,
+               "peer_regions[rank] must be this rank's region");
+  auto* h = new sfem_scalar_exchange();
+  h->rank = rank;
+  h->world = world;
+  h->my_region = (char*)my_region;
+  cudaError_t e = cudaMalloc(&h->d_peer_regions, sizeof(uint64_t) * world);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_timeout, sizeof(unsigned));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(h->d_peer_regions, peer_regions, sizeof(uint64_t) * world,
+                   cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(h->d_timeout, 0, sizeof(unsigned));
+  if (e != cudaSuccess) {
+    set_error(std::string("sfem_scalar_exchange_create: ") +
+              cudaGetErrorString(e));
+    sfem_scalar_exchange_destroy(h);
+    return SFEM_ERR_CUDA;
+  }
+  *out = h;
+  return SFEM_OK;
+}
+
+void sfem_scalar_exchange_destroy(sfem_scalar_exchange* h) {
+  if (!h) return;
+  cudaFree(h->d_peer_regions);
+  cudaFree(h->d_timeout);
+  delete h;
+}
+
+int sfem_scalar_allreduce(sfem_scalar_exchange* h, double* values,
+                          int32_t count, sfem_stream_t stream) {
+  using namespace sfem;
+  SFEM_REQUIRE(h && values, "null argument");
+  SFEM_REQUIRE(count >= 1 && count <= 4, "count must be 1..4");
+  h->epoch += 1;
+  SFEM_CUDA_CHECK(launch_maybe_pdl(
+      true, scalar_allreduce_kernel, dim3(1), dim3(128), 0,
+      (cudaStream_t)stream, values, (int)count, h->rank, h->world,
+      h->my_region, (const uint64_t*)h->d_peer_regions, h->epoch,
+      h->d_timeout));
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_scalar_exchange_timed_out(const sfem_scalar_exchange* h,
+                                   sfem_stream_t stream) {
+  using namespace sfem;
+  SFEM_REQUIRE(h, "null argument");
+  unsigned v = 0;
+  SFEM_CUDA_CHECK(cudaMemcpyAsync(&v, h->d_timeout, sizeof(v),
+                                  cudaMemcpyDeviceToHost,
+                                  (cudaStream_t)stream));
+  SFEM_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  return v != 0 ? 1 : 0;
 }
 
 int sfem_halo_create(const sfem_halo_desc* desc, sfem_halo** halo) {

@@ -664,6 +664,38 @@ def test_peer_memory_halo_single_process(case, dtype):
     assert np.array_equal(ones[r].cpu().numpy(), mult[l2gs[r]])
 
 
+@pytest.mark.parametrize('world', [2, 8])
+def test_peer_memory_scalar_allreduce_single_process(world):
+  """`sfem_scalar_allreduce` with all ranks in one process: each rank's
+  all-reduce runs on its own stream (the single-CTA kernels wait for one
+  another on the device).  Sums in rank order, identical on all ranks, both
+  epoch parities, 1..4 values."""
+  from swirl_fem_b200.communication.scalar_exchange import ScalarExchange
+  device = torch.device('cuda', 0)
+  sx = ScalarExchange.create_local(world, device)
+  streams = [torch.cuda.Stream(device=device) for _ in range(world)]
+  rng = np.random.default_rng(9)
+  for epoch, count in enumerate([1, 2, 4, 1, 3]):
+    host = rng.standard_normal((world, count)) * 10.0 ** rng.integers(
+        -3, 4, size=(world, count))
+    vals = [dev(host[r]) for r in range(world)]
+    torch.cuda.synchronize()
+    for r in range(world):
+      with torch.cuda.stream(streams[r]):
+        sx[r].allreduce_(vals[r])
+    torch.cuda.synchronize()
+    want = np.zeros(count)
+    for r in range(world):   # ascending rank order, as the kernel adds
+      want = want + host[r]
+    for r in range(world):
+      assert not sx[r].timed_out()
+      np.testing.assert_array_equal(vals[r].cpu().numpy(), want)
+  with pytest.raises(ValueError):
+    sx[0].allreduce_(torch.zeros(5, dtype=torch.float64, device=device))
+  with pytest.raises(ValueError):
+    sx[0].allreduce_(torch.zeros(2, dtype=torch.float32, device=device))
+
+
 def test_multi_gpu_partitioned_parity():
   """2 ranks over NCCL vs the unpartitioned solve (needs >= 2 GPUs)."""
   import os

@@ -123,6 +123,21 @@ def main():
     xs, info = distributed_cg(
         op, halo, b_loc, tol=1e-9, minv=minv, check_every=7,
         num_interface_elements=blk.num_interface_elements)
+    # the same solve with the dot products all-reduced over peer memory
+    from swirl_fem_b200.communication.scalar_exchange import ScalarExchange  # noqa: E402
+    sx = ScalarExchange.create(dev)
+    if sx is not None:
+      xs2, info2 = distributed_cg(
+          op, halo, b_loc, tol=1e-9, minv=minv, check_every=7,
+          num_interface_elements=blk.num_interface_elements,
+          scalar_exchange=sx)
+      assert not sx.timed_out(), 'scalar exchange timed out'
+      assert abs(info2['num_iterations'] - info['num_iterations']) <= 1, (
+          info2['num_iterations'], info['num_iterations'])
+      assert float((xs2 - xs).abs().max()) <= 1e-9 * float(xs.abs().max())
+      if rank == 0:
+        print(f'  CG scalars over peer memory: {info2["num_iterations"]} '
+              f'iterations (NCCL: {info["num_iterations"]})', flush=True)
     gb = gop.apply(torch.ones_like(gu), lam=1.0, mu=0.0)
     gx, ginfo = cg(gop.bind(0.0, 1.0), gb, tol=1e-9,
                    M=JacobiPreconditioner(gop.jacobi_minv()))
