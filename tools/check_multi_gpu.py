@@ -125,7 +125,9 @@ def main():
         num_interface_elements=blk.num_interface_elements)
     # the same solve with the dot products all-reduced over peer memory
     from swirl_fem_b200.communication.scalar_exchange import ScalarExchange  # noqa: E402
-    sx = ScalarExchange.create(dev)
+    # (opt-in: SFEM_CHECK_SCALARS=1)
+    sx = (ScalarExchange.create(dev)
+          if os.environ.get('SFEM_CHECK_SCALARS') == '1' else None)
     if sx is not None:
       xs2, info2 = distributed_cg(
           op, halo, b_loc, tol=1e-9, minv=minv, check_every=7,
