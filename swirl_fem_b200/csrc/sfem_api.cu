@@ -134,10 +134,9 @@ int op_apply_internal(const sfem_op* op, double lambda, double mu,
   const bool pdl = op->variant == 0 && d.collocated && d.dim == 3 &&
                    d.n1d <= 16 && (op->n_zero > 0 || dot_xy);
   sfem_op sub = *op;
-  sub.pdl = pdl;
   if (pdl) {
     int rc = launch_zero_fill(y, esz * (size_t)op->n_zero * ncomp, dot_xy,
-                              stream);
+                              stream, &sub.pdl);
     if (rc) return rc;
   } else {
     if (op->n_zero > 0)

@@ -354,7 +354,10 @@ struct sfem_op {
 namespace sfem {
 // Zero fill of y's shared-dof prefix and of the dot accumulator by ONE small
 // kernel (one CTA per SM) that lets its dependents launch at once.
-int launch_zero_fill(void* y, size_t bytes, double* dot_xy, cudaStream_t stream);
+// `*used_kernel` = false when y is not 16-byte aligned and plain memsets were
+// enqueued instead (the apply must then be launched without the attribute).
+int launch_zero_fill(void* y, size_t bytes, double* dot_xy, cudaStream_t stream,
+                     bool* used_kernel);
 // kernel<<<grid, block, smem, stream>>>(args...) with the programmatic stream
 // serialization attribute when `pdl`.
 template <typename... KArgs, typename... Args>

@@ -357,8 +357,9 @@ namespace sfem {
 // y is a torch / XLA allocation (>= 256-byte aligned); the last bytes % 16 are
 // written one by one.
 int launch_zero_fill(void* y, size_t bytes, double* dot_xy,
-                     cudaStream_t stream) {
-  if (((uintptr_t)y & 15u) != 0) {  // unaligned views: plain memsets
+                     cudaStream_t stream, bool* used_kernel) {
+  *used_kernel = ((uintptr_t)y & 15u) == 0;
+  if (!*used_kernel) {  // unaligned views: plain memsets
     if (bytes) SFEM_CUDA_CHECK(cudaMemsetAsync(y, 0, bytes, stream));
     if (dot_xy)
       SFEM_CUDA_CHECK(cudaMemsetAsync(dot_xy, 0, sizeof(double), stream));

@@ -473,10 +473,10 @@ int sfem_op_apply_halo(const sfem_op* op, sfem_halo* halo, double lambda,
     return sfem_halo_push(halo, y, stream_);
   }
   const size_t esz = d.dtype == SFEM_F64 ? 8 : 4;
-  const bool pdl = op->n_zero > 0 || dot_xy;
+  bool pdl = op->n_zero > 0 || dot_xy;
   if (pdl) {
     int rc = launch_zero_fill(y, esz * (size_t)op->n_zero, (double*)dot_xy,
-                              stream);
+                              stream, &pdl);
     if (rc) return rc;
   }
   HaloDev hd = begin_epoch(halo, num_interface_elements);
