@@ -204,3 +204,29 @@ class StokesSEM:
                           tol=tol, atol=atol, dot_fn=dot)
     u = u_star + self.Q(self.Dt(dp), dt, time_order)
     return u, p_ext + dp, {'u_star_info': info_u, 'dp_info': info_p}
+
+
+def kolmogorov_forcing(x, u, drag_coeff=0.1):
+  """niles/datagen/datagen.py:65-72."""
+  f0 = np.sin(2 * np.pi * 4. * x[:, 1])
+  return np.stack([f0, np.zeros_like(f0)], -1) - drag_coeff * u
+
+
+def kolmogorov_u_init(x):
+  """niles/datagen/datagen.py:56-62."""
+  l = 2.
+  return np.stack(
+      [np.cos(2 * l * np.pi * x[:, 0]) * np.sin(2 * l * np.pi * x[:, 1]),
+       -np.sin(2 * l * np.pi * x[:, 0]) * np.cos(2 * l * np.pi * x[:, 1])], -1)
+
+
+def navier_stokes_one_step(sem: StokesSEM, us, ps, Cus, reynolds_number, dt,
+                           time_order, drag_coeff=0.1, tol=1e-5, atol=1e-4):
+  """`_solve_one_step` of niles/datagen/datagen.py:88-102."""
+  ext = extk_coeffs(time_order - 1)
+  Cu = sum(ext[-i] * Cus[-i] for i in range(1, len(ext) + 1))
+  f = kolmogorov_forcing(sem.vmesh['node_coords'], us[-1], drag_coeff)
+  f = -Cu + sem.B(f)
+  u, p, aux = sem.stokes_one_step(us, ps, f, mu=1 / reynolds_number, dt=dt,
+                                  time_order=time_order, tol=tol, atol=atol)
+  return u, p, sem.C(u), aux

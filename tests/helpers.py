@@ -99,7 +99,7 @@ def stokes_vortices_premesh(ne=9, curved=0.0):
   return pm.replace(node_coords=x)
 
 
-def stokes_oracle_meshes(premesh, order):
+def stokes_oracle_meshes(premesh, order, boundary='boundary'):
   """Host meshes (numpy) of the velocity (GLL) and pressure (GL) spaces for
   `oracle.dense_ns.StokesSEM`, built with the host mesh code that the
   connectivity goldens pin bit-exactly to the reference."""
@@ -107,7 +107,8 @@ def stokes_oracle_meshes(premesh, order):
   pref = refine_premesh(premesh, Nodes1D.create(order - 1, GL))
   vhost = vref.finalize_host()
   vmesh = dict(node_coords=vref.node_coords, elements=vref.elements,
-               interior_mask=1.0 - vhost['physical_masks']['boundary'],
+               interior_mask=(1.0 - vhost['physical_masks'][boundary]
+                              if boundary else np.ones(vref.num_nodes)),
                exchange_gather_indices=vhost['exchange_gather_indices'],
                exchange_unique_indices=vhost['exchange_unique_indices'])
   pmesh = dict(node_coords=pref.node_coords, elements=pref.elements)

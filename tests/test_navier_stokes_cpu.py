@@ -152,3 +152,27 @@ def test_solve_one_step(vortices):
   assert np.abs(p - ps[-1]).max() < 50 * dt ** 2
   assert aux['u_star_info']['residual'] < 1e-7
   assert aux['dp_info']['residual'] < 1e-7
+
+
+def test_kolmogorov_step_on_the_oracle():
+  """The Navier-Stokes step of the reference's data generator
+  (niles/datagen/datagen.py:88-102) on the doubly periodic square: the flow
+  stays divergence free (to the solver tolerance) and the initial
+  Taylor-Green-like state decays slowly at high Reynolds number."""
+  from swirl_fem_b200.common.premesh_commons import unit_cube_mesh
+  pm = unit_cube_mesh(4, ndim=2, periodic_dims=(0, 1))
+  order, k, dt = 6, 3, 1e-3
+  vmesh, pmesh = helpers.stokes_oracle_meshes(pm, order, boundary=None)
+  sem = dense_ns.StokesSEM(vmesh, pmesh, order)
+  u0 = dense_ns.kolmogorov_u_init(vmesh['node_coords'])
+  us = (u0,) * k
+  ps = (np.zeros(pmesh['node_coords'].shape[0]),) * k
+  Cus = tuple(sem.C(u) for u in us)
+  for _ in range(2):
+    u, p, Cu, aux = dense_ns.navier_stokes_one_step(
+        sem, us, ps, Cus, reynolds_number=1000., dt=dt, time_order=k,
+        tol=1e-9, atol=1e-12)
+    us, ps, Cus = us[1:] + (u,), ps[1:] + (p,), Cus[1:] + (Cu,)
+  assert np.isfinite(u).all() and np.isfinite(p).all()
+  assert np.abs(sem.D(u)).max() < 1e-6
+  assert 0.9 < np.abs(u).max() / np.abs(u0).max() < 1.1
