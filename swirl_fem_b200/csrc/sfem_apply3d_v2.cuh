@@ -220,8 +220,33 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc,
 // finds nothing left to do.  Nothing ever spins: a CTA that exits before a
 // condition holds leaves its slices to the CTAs that are still running (the
 // last signaller always is) or, for the sum, to the wait kernel.
+// Same copy with an L2 evict-first policy: the factors are read exactly once,
+// so they should not push x / y lines (which ARE re-used by neighbouring
+// elements a few steps later) out of L2.  [experimental variant, see launch3d_v2]
+__device__ __forceinline__ void bulk_copy_g2s_evict_first(void* smem_dst,
+                                                          const void* gsrc,
+                                                          unsigned bytes,
+                                                          uint64_t* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;"
+               : "=l"(policy));
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(d),
+      "l"(gsrc), "r"(bytes), "r"(b), "l"(policy)
+      : "memory");
+}
+
+// CONN2 / EVICT are tuning variants (SFEM_EXPERIMENTS builds only):
+//   CONN2: the connectivity words are fetched TWO element steps ahead (ncu on
+//          the default kernel: 21 % of all stall samples sit on the first use
+//          of the next element's connectivity, a DRAM load issued only one
+//          barrier earlier);
+//   EVICT: factors staged with the evict-first copy above.
 template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH,
-          bool HALO = false>
+          bool HALO = false, bool CONN2 = false, bool EVICT = false>
 __global__ void __launch_bounds__((Cfg3DV2<T, N, EPB, MINB, KCH>::threads),
                                   MINB)
 apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
@@ -280,7 +305,11 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     const int64_t count = (E - first) < epb ? (E - first) : epb;
     const unsigned bytes = ((unsigned)count * gbytes + 15u) & ~15u;
     mbar_expect_tx(&gbar, bytes);
-    bulk_copy_g2s(sG0, gf + first * (int64_t)(ngeom * n), bytes, &gbar);
+    if constexpr (EVICT)
+      bulk_copy_g2s_evict_first(sG0, gf + first * (int64_t)(ngeom * n), bytes,
+                                &gbar);
+    else
+      bulk_copy_g2s(sG0, gf + first * (int64_t)(ngeom * n), bytes, &gbar);
   };
   if (STAGE) {
     if (threadIdx.x == 0) mbar_init(&gbar, 1);
@@ -340,6 +369,17 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
   pdl_launch_dependents();
   bool first_step = true;
 
+  // CONN2: connectivity of the NEXT step, carried across iterations
+  uint32_t nrc_c[CONN2 ? N : 1];
+  if constexpr (CONN2 && !LOCAL) {
+    const int64_t blk1 = blk + gridDim.x;
+    const int64_t e1 = blk1 * epb + slot;
+    const bool a1 = lane_ok && blk1 < nblocks && e1 < E;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      nrc_c[k] = a1 ? ld_stream(conn + e1 * n + k * P + t) : kConnSentinel;
+  }
+
   int buf = 0;
   for (; blk < nblocks; blk += gridDim.x, buf ^= 1) {
     T* sU = sU0 + buf * C::tile;
@@ -351,6 +391,19 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     uint32_t nrc[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) nrc[k] = kConnSentinel;
+    if constexpr (CONN2 && !LOCAL) {
+      // this step's "next" words arrived a whole step ago; fetch the ones of
+      // the step after it
+      const int64_t blk_nn = blk_n + gridDim.x;
+      const int64_t e_nn = blk_nn * epb + slot;
+      const bool active_nn = lane_ok && blk_nn < nblocks && e_nn < E;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        nrc[k] = nrc_c[k];
+        nrc_c[k] = active_nn ? ld_stream(conn + e_nn * n + k * P + t)
+                             : kConnSentinel;
+      }
+    }
     if (active_n) {
       if (!STAGE) {
         const char* g =
@@ -360,7 +413,7 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
         for (int l = 0; l < (lines + P - 1) / P; ++l)
           if (l * P + t < lines) prefetch_l2(g + (int64_t)(l * P + t) * 128);
       }
-      if (!LOCAL) {
+      if (!LOCAL && !CONN2) {
 #pragma unroll
         for (int k = 0; k < N; ++k)
           nrc[k] = ld_stream(conn + e_n * n + k * P + t);
@@ -646,7 +699,7 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
 }
 
 template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH,
-          bool HALO = false>
+          bool HALO = false, bool CONN2 = false, bool EVICT = false>
 int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
                     void* y, int ncomp, double* dot_xy, cudaStream_t stream) {
   using C = Cfg3DV2<T, N, EPB, MINB, KCH>;
@@ -656,7 +709,8 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
       ((size_t)C::stage_off(C::epb) +
        (KCH == 0 ? (size_t)C::epb * (MASS ? 7 : 6) * C::n : 0)) *
       sizeof(T);
-  auto kernel = apply3d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB, KCH, HALO>;
+  auto kernel =
+      apply3d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB, KCH, HALO, CONN2, EVICT>;
   static int per_sm = 0;
   if (per_sm == 0) {
     if (smem > 48 * 1024)
@@ -787,6 +841,18 @@ int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
       case 8:  // no staging: factors streamed from L2 in batches of 2 slabs
         return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, 2>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
+      case 9:  // connectivity fetched two steps ahead
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
+                               true, false>(op, lambda, mu, x, y, ncomp, dot_xy,
+                                            stream);
+      case 10:  // factors staged with an L2 evict-first policy
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
+                               false, true>(op, lambda, mu, x, y, ncomp, dot_xy,
+                                            stream);
+      case 11:  // both
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
+                               true, true>(op, lambda, mu, x, y, ncomp, dot_xy,
+                                           stream);
       default:
         break;
     }
