@@ -48,74 +48,108 @@ from swirl_fem_b200.linalg.cg import cg
 # pylint: disable=invalid-name
 
 
+def _history_interpolator(k: int, at: float) -> BarycentricInterpolator:
+  """Lagrange basis of the last k+1 time levels, mapped to the equispaced
+  points of [-1, 1] (the newest level sits at +1, the step is 2/k), evaluated
+  at the abscissa `at`."""
+  levels = Nodes1D.create(num_points=k + 1, node_type=NodeType.NEWTON_COTES)
+  target = Nodes1D.create_single_point(
+      node_value=np.array(at, dtype=np.float64))
+  return BarycentricInterpolator(ndim=1, gridpoints_1d=levels,
+                                 evalpoints_1d=target)
+
+
 def extk_coeffs(k: int) -> np.ndarray:
-  """Linear extrapolation coefficients of order k (navier_stokes.py:48-57)."""
-  gridpoints = Nodes1D.create(num_points=k + 1, node_type=NodeType.NEWTON_COTES)
-  h = 2 / k
-  evalpoints = Nodes1D.create_single_point(
-      node_value=np.array(1 + h, dtype=np.float64))
-  interpolator = BarycentricInterpolator(
-      ndim=1, gridpoints_1d=gridpoints, evalpoints_1d=evalpoints)
-  return interpolator.interpolation_matrix().reshape((-1))
+  """EXT-k weights: the k+1 stored levels extrapolated one step ahead
+  (reference `extk_coeffs`, navier_stokes.py:48-57)."""
+  step = 2 / k
+  return _history_interpolator(k, 1 + step).interpolation_matrix().reshape(-1)
 
 
 def bdfk_coeffs(k: int) -> np.ndarray:
-  """Backward differentiation formula of order k (navier_stokes.py:60-70)."""
-  gridpoints = Nodes1D.create(num_points=k + 1, node_type=NodeType.NEWTON_COTES)
-  evalpoints = Nodes1D.create_single_point(
-      node_value=np.array(1., dtype=np.float64))
-  interpolator = BarycentricInterpolator(
-      ndim=1, gridpoints_1d=gridpoints, evalpoints_1d=evalpoints)
-  h = 2 / k
-  return interpolator.interpolation_matrix_grad().reshape((-1)) * h
+  """BDF-k weights: d/dt at the newest level in units of 1/dt, oldest level
+  first (reference `bdfk_coeffs`, navier_stokes.py:60-70)."""
+  step = 2 / k
+  slope = _history_interpolator(k, 1.).interpolation_matrix_grad().reshape(-1)
+  return slope * step
 
 
 def _pressure_project_out_nullspace(sem, p):
-  """Remove the nullspace (all 1s vector) from p (navier_stokes.py:73-78)."""
-  w = sem.pressure.exchange(p)
-  q = torch.ones_like(p)
-  num = _lib.dot(q, sem.pressure.B(w))
-  den = _lib.dot(q, sem.pressure.B(q))
-  return w - (num / den).to(p.dtype) * q
+  """Subtracts the constant mode (mass-weighted mean) from a pressure field;
+  the preconditioner of the singular pressure system
+  (navier_stokes.py:73-78).  Both dot products are the device `sfem_dot`."""
+  shared = sem.pressure.exchange(p)
+  constant = torch.ones_like(p)
+  mean = (_lib.dot(constant, sem.pressure.B(shared)) /
+          _lib.dot(constant, sem.pressure.B(constant)))
+  return shared - mean.to(p.dtype) * constant
 
 
 @enum.unique
 class BCType(enum.Enum):
-  """Types of boundary conditions (navier_stokes.py:81-85)."""
+  """Kinds of boundary condition a physical group can carry (:81-85)."""
   DIRICHLET = 'dirichlet'
   NEUMANN = 'neumann'
 
 
 def dirichlet_bc(mesh: Mesh, boundary_conditions) -> torch.Tensor:
-  """Interior mask from the boundary conditions (navier_stokes.py:88-94)."""
-  interior_mask = torch.ones(mesh.num_nodes, dtype=mesh.node_coords.dtype,
-                             device=mesh.device)
-  for physical_group, (bctype, unused_bcvalue) in boundary_conditions.items():
-    if bctype == BCType.DIRICHLET:
-      interior_mask = interior_mask * (
-          1 - mesh.physical_masks[physical_group].to(interior_mask.dtype))
-  return interior_mask
+  """1 on free nodes, 0 on every node of a Dirichlet group (:88-94)."""
+  free = torch.ones(mesh.num_nodes, dtype=mesh.node_coords.dtype,
+                    device=mesh.device)
+  constrained = [name for name, (kind, _) in boundary_conditions.items()
+                 if kind == BCType.DIRICHLET]
+  for name in constrained:
+    free = free * (1 - mesh.physical_masks[name].to(free.dtype))
+  return free
+
+
+# Bilinear / trilinear forms in the convention of `core.fespace` (a form takes
+# q-functions and returns the pointwise integrand).
+def _MASS_FORM(u, v):
+  return lambda x: u(x) * v(x)
+
+
+def _VECTOR_MASS_FORM(u, v):
+  return lambda x: (u(x) * v(x)).sum(0)
+
+
+def _VECTOR_STIFFNESS_FORM(u, v):
+  return lambda x: (grad(u)(x) * grad(v)(x)).sum((0, 1))
+
+
+def _DIVERGENCE_FORM(v, q):
+  return lambda x: div(v)(x) * q(x)
+
+
+def _CONVECTION_FORM(u, w, v):
+  def integrand(x):
+    ux, gw, vx = u(x), grad(w)(x), v(x)
+    d = ux.shape[0]
+    return sum(ux[i] * gw[i, j] * vx[j] for i in range(d) for j in range(d))
+  return integrand
 
 
 def _vmap_last(fn, u: torch.Tensor) -> torch.Tensor:
-  """`vmap(fn, in_axes=-1, out_axes=-1)(u)` for a scalar-field kernel call."""
+  """Applies a scalar-field kernel call to every component of an AoS field
+  (the reference vmaps over the last axis)."""
   return torch.stack([fn(u[..., k].contiguous()) for k in range(u.shape[-1])],
                      dim=-1)
 
 
 @dataclasses.dataclass
 class StokesPressure:
-  """Pressure space for the Stokes problem (navier_stokes.py:97-139)."""
+  """Discontinuous pressure: `order - 1` Gauss-Legendre points per axis,
+  integrated with the velocity's quadrature rule (navier_stokes.py:97-139)."""
   pspace: FiniteElementSpace
 
   @classmethod
   def create(cls, premesh: Premesh, quadrature: Quadrature1D, order: int,
              device=None, dtype=None) -> 'StokesPressure':
-    gridpoints_1d = Nodes1D.create(
-        num_points=order - 1, node_type=NodeType.GAUSS_LEGENDRE)
-    pmesh = refine_premesh(premesh, gridpoints_1d=gridpoints_1d).finalize(
+    gl_points = Nodes1D.create(num_points=order - 1,
+                               node_type=NodeType.GAUSS_LEGENDRE)
+    mesh = refine_premesh(premesh, gridpoints_1d=gl_points).finalize(
         device=device, dtype=dtype)
-    return cls(pspace=FiniteElementSpace.create(mesh=pmesh,
+    return cls(pspace=FiniteElementSpace.create(mesh=mesh,
                                                 quadrature=quadrature))
 
   def gather(self, p):
@@ -125,22 +159,21 @@ class StokesPressure:
     return self.pspace.mesh.scatter(p)
 
   def B(self, p):
-    """Apply the pressure mass matrix."""
-    def l(u, v):
-      return lambda x: u(x) * v(x)
-
-    u = self.pspace.scalar_function(self.gather(p))
-    v = self.pspace.scalar_function(None)
-    return self.scatter(self.pspace.local_covector(l, (u, v)))
+    """Consistent pressure mass matrix (classified as a mass form -> fused
+    local operator kernel)."""
+    trial = self.pspace.scalar_function(self.gather(p))
+    test = self.pspace.scalar_function(None)
+    return self.scatter(self.pspace.local_covector(_MASS_FORM, (trial, test)))
 
   def exchange(self, p):
-    """Apply QQ^T."""
+    """QQ^T on the pressure mesh (no shared dofs unless periodic)."""
     return self.pspace.mesh.exchange(p)
 
 
 @dataclasses.dataclass
 class StokesVelocity:
-  """Velocity space for the Stokes system (navier_stokes.py:142-245)."""
+  """Continuous GLL velocity of order `order`, its collocated rule and the
+  over-integration rule of the convection term (navier_stokes.py:142-245)."""
   vspace: FiniteElementSpace
   overint_space: FiniteElementSpace
   interior_mask: torch.Tensor   # (G, 1)
@@ -151,25 +184,26 @@ class StokesVelocity:
   def create(cls, premesh: Premesh, order: int, boundary_conditions,
              num_convection_overint_nodes: int = 2, device=None,
              dtype=None) -> 'StokesVelocity':
-    gridpoints_1d = Nodes1D.create(
-        num_points=order + 1, node_type=NodeType.GAUSS_LOBATTO_LEGENDRE)
-    vmesh = refine_premesh(premesh, gridpoints_1d=gridpoints_1d).finalize(
+    gll = NodeType.GAUSS_LOBATTO_LEGENDRE
+    nodes = Nodes1D.create(num_points=order + 1, node_type=gll)
+    mesh = refine_premesh(premesh, gridpoints_1d=nodes).finalize(
         device=device, dtype=dtype)
-    vspace = FiniteElementSpace.create(
-        mesh=vmesh,
-        quadrature=Quadrature1D.create_from_nodes_1d(gridpoints_1d))
-    interior_mask = dirichlet_bc(vmesh, boundary_conditions)[:, None]
-    overint_gridpoints_1d = Nodes1D.create(
-        num_points=gridpoints_1d.num_points + num_convection_overint_nodes,
-        node_type=NodeType.GAUSS_LOBATTO_LEGENDRE)
-    overint_space = FiniteElementSpace.create(
-        mesh=vmesh,
-        quadrature=Quadrature1D.create_from_nodes_1d(overint_gridpoints_1d))
-    diag_qqt = vmesh.scatter(torch.ones(
-        tuple(vmesh.elements.shape), dtype=vmesh.node_coords.dtype,
-        device=vmesh.device))
-    return cls(vspace=vspace, overint_space=overint_space, diag_qqt=diag_qqt,
-               interior_mask=interior_mask,
+
+    def space_with(points: Nodes1D) -> FiniteElementSpace:
+      return FiniteElementSpace.create(
+          mesh=mesh, quadrature=Quadrature1D.create_from_nodes_1d(points))
+
+    finer = Nodes1D.create(
+        num_points=nodes.num_points + num_convection_overint_nodes,
+        node_type=gll)
+    # multiplicity of every node over the elements (weights of the filter and
+    # of the vorticity average)
+    multiplicity = mesh.scatter(torch.ones(
+        tuple(mesh.elements.shape), dtype=mesh.node_coords.dtype,
+        device=mesh.device))
+    return cls(vspace=space_with(nodes), overint_space=space_with(finer),
+               diag_qqt=multiplicity,
+               interior_mask=dirichlet_bc(mesh, boundary_conditions)[:, None],
                num_convection_overint_nodes=num_convection_overint_nodes)
 
   @property
@@ -182,7 +216,7 @@ class StokesVelocity:
     return self.vspace.mesh
 
   def C(self, u):
-    """Apply the convection operator with overintegration."""
+    """Assembled, masked convection term `(u . grad) u` (over-integrated)."""
     return self.interior_mask * self.scatter(self.C_local(self.gather(u)))
 
   def gather(self, u):
@@ -192,29 +226,24 @@ class StokesVelocity:
     return _vmap_last(self.vspace.mesh.scatter, u)
 
   def exchange(self, u):
-    """Apply QQ^T."""
+    """QQ^T per component (periodic / shared dofs get the sum of their copies)."""
     return _vmap_last(self.vspace.mesh.exchange, u)
 
-  def A_local(self, u_local):
-    """Apply the velocity stiffness operator locally."""
-    def a(u, v):
-      return lambda x: (grad(u)(x) * grad(v)(x)).sum((0, 1))
+  def _vector_covector(self, form, u_local):
+    trial = self.vspace.vector_function(u_local)
+    return self.vspace.local_covector(
+        form, (trial, self.vspace.vector_function(None)))
 
-    u = self.vspace.vector_function(u_local)
-    v = self.vspace.vector_function(None)
-    return self.vspace.local_covector(a, (u, v))
+  def A_local(self, u_local):
+    """Element-local vector stiffness (classified -> fused local kernel)."""
+    return self._vector_covector(_VECTOR_STIFFNESS_FORM, u_local)
 
   def B_local(self, u_local):
-    """Apply the velocity mass operator locally."""
-    def l(u, v):
-      return lambda x: (u(x) * v(x)).sum(0)
-
-    u = self.vspace.vector_function(u_local)
-    v = self.vspace.vector_function(None)
-    return self.vspace.local_covector(l, (u, v))
+    """Element-local vector mass (classified -> fused local kernel)."""
+    return self._vector_covector(_VECTOR_MASS_FORM, u_local)
 
   def C_local(self, u_local):
-    """Apply the local convection operator: u_i d_i w_j v_j.
+    """Element-local convection covector of `u_i d_i u_j v_j`.
 
     Fixed form -> three kernels (values and gradients on the over-integration
     rule, `(u . grad) u` pointwise, transposed evaluation);
@@ -229,22 +258,16 @@ class StokesVelocity:
 
   def C_local_general(self, u_local):
     """`C_local` through `local_covector` (navier_stokes.py:238-245)."""
-    def c(u, w, v):
-      def f(x):
-        ux, gw, vx = u(x), grad(w)(x), v(x)
-        d = ux.shape[0]
-        return sum(ux[i] * gw[i, j] * vx[j]
-                   for i in range(d) for j in range(d))
-      return f
-
-    u = self.overint_space.vector_function(u_local)
-    v = self.overint_space.vector_function(None)
-    return self.overint_space.local_covector(c, (u, u, v))
+    sp = self.overint_space
+    field = sp.vector_function(u_local)
+    return sp.local_covector(_CONVECTION_FORM,
+                             (field, field, sp.vector_function(None)))
 
 
 @dataclasses.dataclass
 class StokesSEM:
-  """Linear operators of the spectral-element Stokes solver (:248-495)."""
+  """The P_N / P_{N-2} spectral-element Stokes operators and the fractional
+  step built from them (navier_stokes.py:248-495)."""
 
   velocity: StokesVelocity
   pressure: StokesPressure
@@ -257,18 +280,20 @@ class StokesSEM:
              dtype=None) -> 'StokesSEM':
     if premesh.order != 1:
       raise ValueError(f'Expected mesh order 1; got {premesh.order}.')
-    quadrature = Quadrature1D.create(
-        num_points=order + 1, quadrature_type=NodeType.GAUSS_LOBATTO_LEGENDRE)
-    pressure = StokesPressure.create(premesh, quadrature, order,
-                                     device=device, dtype=dtype)
     velocity = StokesVelocity.create(
         premesh, order, boundary_conditions, num_convection_overint_nodes,
         device=device, dtype=dtype)
-    ones = torch.ones(velocity.local_shape, dtype=velocity.vspace.dtype,
-                      device=velocity.mesh.device)
-    velocity_mass_diag = velocity.scatter(velocity.B_local(ones))
+    # the pressure is integrated with the velocity's collocated GLL rule
+    shared_rule = Quadrature1D.create(
+        num_points=order + 1, quadrature_type=NodeType.GAUSS_LOBATTO_LEGENDRE)
+    pressure = StokesPressure.create(premesh, shared_rule, order,
+                                     device=device, dtype=dtype)
+    # lumped (diagonal) velocity mass: rows sums of the consistent matrix
+    unit_field = torch.ones(velocity.local_shape, dtype=velocity.vspace.dtype,
+                            device=velocity.mesh.device)
+    lumped = velocity.scatter(velocity.B_local(unit_field))
     return cls(velocity=velocity, pressure=pressure,
-               velocity_mass_diag=velocity_mass_diag)
+               velocity_mass_diag=lumped)
 
   # -- fused velocity operator (hot path) ----------------------------------
   def _velocity_operator(self):
@@ -282,23 +307,26 @@ class StokesSEM:
     return op
 
   def B(self, u):
-    """Apply the mass operator to a velocity field."""
+    """Lumped velocity mass with Dirichlet rows removed."""
     return self.velocity.interior_mask * self.velocity_mass_diag * u
 
   def Bi(self, u):
-    """Apply the inverse mass operator to a velocity field."""
-    diag_qqti = self._cache.get('diag_qqti')
-    if diag_qqti is None:  # (the reference re-exchanges it on every call)
-      diag_qqti = 1 / self.velocity.exchange(self.velocity_mass_diag)
-      self._cache['diag_qqti'] = diag_qqti
-    return diag_qqti * self.velocity.exchange(u)
+    """Inverse of the assembled lumped mass applied to an un-assembled field:
+    `QQ^T u / QQ^T diag`.  The assembled diagonal is cached (the reference
+    exchanges it again on every call)."""
+    inverse = self._cache.get('diag_qqti')
+    if inverse is None:
+      inverse = 1 / self.velocity.exchange(self.velocity_mass_diag)
+      self._cache['diag_qqti'] = inverse
+    return inverse * self.velocity.exchange(u)
 
   def A(self, u):
-    """Apply the stiffness operator to a velocity field (fused kernel)."""
+    """Masked vector Laplacian: ONE fused launch (gather, sum-factorised
+    stiffness, scatter, Dirichlet rows) for all components."""
     return self._velocity_operator().apply(u.contiguous(), lam=0.0, mu=1.0)
 
   def C(self, u):
-    """Apply the convection operator to a velocity field."""
+    """Convection term, see `StokesVelocity.C`."""
     return self.velocity.C(u)
 
   def D_local(self, u_local):
@@ -326,40 +354,36 @@ class StokesSEM:
 
   def D_local_general(self, u_local):
     """`D_local` through `local_covector` (navier_stokes.py:313-320)."""
-    def b(v, q):
-      return lambda x: div(v)(x) * q(x)
-
-    v = self.velocity.vspace.vector_function(u_local)
-    p = self.pressure.pspace.scalar_function(None)
-    return self.pressure.pspace.local_covector(b, (v, p))
+    vs, ps = self.velocity.vspace, self.pressure.pspace
+    return ps.local_covector(
+        _DIVERGENCE_FORM,
+        (vs.vector_function(u_local), ps.scalar_function(None)))
 
   def Dt_local_general(self, p_local):
     """`Dt_local` through `local_covector` (navier_stokes.py:322-329)."""
-    def b(v, q):
-      return lambda x: div(v)(x) * q(x)
-
-    v = self.velocity.vspace.vector_function(None)
-    p = self.pressure.pspace.scalar_function(p_local)
-    return self.velocity.vspace.local_covector(b, (v, p))
+    vs, ps = self.velocity.vspace, self.pressure.pspace
+    return vs.local_covector(
+        _DIVERGENCE_FORM,
+        (vs.vector_function(None), ps.scalar_function(p_local)))
 
   def D(self, u):
-    """Velocity divergence matrix."""
+    """Discrete divergence: velocity (G_v, d) -> pressure covector (G_p,)."""
     return self.pressure.scatter(self.D_local(self.velocity.gather(u)))
 
   def Dt(self, p):
-    """Apply the pressure gradient operator."""
+    """Discrete (weak) pressure gradient, the transpose of `D`, masked."""
     return self.velocity.interior_mask * self.velocity.scatter(
         self.Dt_local(self.pressure.gather(p)))
 
   def Q(self, u, dt: float, time_order: int):
-    """Apply the operator Q = (dt / beta_k) B^-1."""
-    beta_k = bdfk_coeffs(time_order)[-1]
-    return (dt / beta_k) * self.Bi(u)
+    """`(dt / beta_k) B^-1`: the approximate inverse of the Helmholtz operator
+    used by the pressure correction."""
+    leading = bdfk_coeffs(time_order)[-1]
+    return (dt / leading) * self.Bi(u)
 
   def E(self, p, dt: float, time_order: int):
-    """Apply the operator E = D Q D^T."""
-    Q_ = partial(self.Q, dt=dt, time_order=time_order)
-    return self.D(Q_(self.Dt(p)))
+    """Pressure operator `D Q D^T` (symmetric, singular on constants)."""
+    return self.D(self.Q(self.Dt(p), dt=dt, time_order=time_order))
 
   def stokes_one_step(
       self, us: Sequence[torch.Tensor], ps: Sequence[torch.Tensor], f,
@@ -367,49 +391,50 @@ class StokesSEM:
       u_boundary: torch.Tensor | None = None, pressure_preconditioner=None,
       project_out_nullspace=True, tol: float = 1e-8, atol: float = 0,
   ) -> tuple[torch.Tensor, torch.Tensor, Any]:
-    """One step of the fractional-step scheme (navier_stokes.py:350-458)."""
+    """One step of the fractional-step scheme (navier_stokes.py:350-458).
+
+    1. tentative velocity: `H u* = f + D^T p_ext - B(sum_j beta_j u^{n-j})/dt`
+       with `H = (beta_k/dt) B + mu A` (CG, `M = exchange`);
+    2. filter `u*`; 3. pressure increment: `E dp = -D u*` (CG with the
+    null-space projector); 4. `u = u* + Q D^T dp`, `p = p_ext + dp`.
+    Returns `(u, p, {'u_star_info', 'dp_info'})`.
+    """
     if pressure_preconditioner is None and project_out_nullspace:
       pressure_preconditioner = partial(_pressure_project_out_nullspace, self)
 
-    # Extrapolate pressure linearly.
-    ext_coeffs = extk_coeffs(k=1)
-    p_ext = sum(
-        float(ext_coeffs[-i]) * ps[-i] for i in range(1, len(ext_coeffs) + 1))
-    f = f + self.Dt(p_ext)
+    # EXT-1 pressure; its gradient joins the right-hand side
+    ext = extk_coeffs(k=1)
+    p_ext = sum(float(ext[-j]) * ps[-j] for j in range(1, len(ext) + 1))
+    rhs = f + self.Dt(p_ext)
 
-    # Solve for H(u*) = b.
-    beta_hist = bdfk_coeffs(time_order)[:-1]
-    beta_k = float(bdfk_coeffs(time_order)[-1])
-    op = self._velocity_operator()
-    mass = self.velocity.interior_mask * self.velocity_mass_diag
+    # BDF-k: the stored levels move to the right-hand side
+    bdf = bdfk_coeffs(time_order)
+    shift = float(bdf[-1]) / dt
+    history = sum(float(weight) * level for weight, level in zip(bdf[:-1], us))
+    rhs = rhs - self.B((1 / dt) * history)
 
-    def H_(u):  # (beta_k / dt) B(u) + mu A(u), A by the fused kernel
-      return (beta_k / dt) * mass * u + op.apply(u.contiguous(), lam=0.0,
-                                                 mu=float(mu))
+    fused = self._velocity_operator()
+    lumped = self.velocity.interior_mask * self.velocity_mass_diag
+    viscosity = float(mu)
 
-    f = f - self.B((1 / dt) * sum(float(coef) * u
-                                  for coef, u in zip(beta_hist, us)))
+    def helmholtz(v):  # shift * B(v) + mu * A(v); A is the fused kernel
+      return shift * lumped * v + fused.apply(v.contiguous(), lam=0.0,
+                                              mu=viscosity)
+
     if u_boundary is not None:
-      f = f - H_(u_boundary)
-
-    u_star, info = cg(H_, f, M=self.velocity.exchange, tol=tol, atol=atol)
+      rhs = rhs - helmholtz(u_boundary)
+    u_star, velocity_info = cg(helmholtz, rhs, M=self.velocity.exchange,
+                               tol=tol, atol=atol)
     if u_boundary is not None:
       u_star = u_star + u_boundary
-    aux = dict()
-    aux['u_star_info'] = info
-
-    # Filter-based stabilization (alpha = 0.05)
     u_star = self.filter(u_star, alpha=alpha)
 
-    # Obtain dp by solving D Q D^T (dp) = -D u*.
-    dp, info = cg(partial(self.E, dt=dt, time_order=time_order),
-                  -self.D(u_star), M=pressure_preconditioner, tol=tol,
-                  atol=atol)
-    aux['dp_info'] = info
-
-    u = u_star + self.Q(self.Dt(dp), dt=dt, time_order=time_order)
-    p = p_ext + dp
-    return u, p, aux
+    dp, pressure_info = cg(partial(self.E, dt=dt, time_order=time_order),
+                           -self.D(u_star), M=pressure_preconditioner,
+                           tol=tol, atol=atol)
+    u_new = u_star + self.Q(self.Dt(dp), dt=dt, time_order=time_order)
+    return u_new, p_ext + dp, {'u_star_info': velocity_info,
+                               'dp_info': pressure_info}
 
   def _filter_space(self):
     """A space whose 'quadrature points' are the grid nodes and whose 1-D
