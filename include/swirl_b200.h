@@ -289,7 +289,10 @@ typedef struct {
 
 typedef struct sfem_halo sfem_halo;
 
-/* All device arrays of the descriptor must outlive the handle. */
+/* All device arrays of the descriptor must outlive the handle.  Unlike
+ * sfem_op, a sfem_halo is a STATEFUL endpoint (epoch counter, device
+ * counters): calls on one handle must be issued from one host thread at a
+ * time and on one stream, in the same order on every rank. */
 int sfem_halo_create(const sfem_halo_desc* desc, sfem_halo** halo);
 void sfem_halo_destroy(sfem_halo* halo);
 
