@@ -813,6 +813,25 @@ int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
   constexpr int EPB = default_epb3d<T, N, MASS>();
   using A = AutoCfg3D<T, N, MASS, EPB>;
 #ifdef SFEM_EXPERIMENTS
+  // pipeline variants for every precision and order (Laplacian, global form)
+  if constexpr (!MASS && !LOCAL) {
+    switch (op.variant) {
+      case 9:  // connectivity fetched two steps ahead
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
+                               true, false>(op, lambda, mu, x, y, ncomp, dot_xy,
+                                            stream);
+      case 10:  // factors staged with an L2 evict-first policy
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
+                               false, true>(op, lambda, mu, x, y, ncomp, dot_xy,
+                                            stream);
+      case 11:  // both
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
+                               true, true>(op, lambda, mu, x, y, ncomp, dot_xy,
+                                           stream);
+      default:
+        break;
+    }
+  }
   // tuning variants (relative to the default), fp64 Laplacian, N = 5..9 only
   if constexpr (sizeof(T) == 8 && N >= 5 && N <= 9 && !MASS && !LOCAL) {
     constexpr int Ep = clamp_int(EPB + 1, 1, 16), Em = clamp_int(EPB - 1, 1, 16);
@@ -841,18 +860,6 @@ int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
       case 8:  // no staging: factors streamed from L2 in batches of 2 slabs
         return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, 2>(
             op, lambda, mu, x, y, ncomp, dot_xy, stream);
-      case 9:  // connectivity fetched two steps ahead
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
-                               true, false>(op, lambda, mu, x, y, ncomp, dot_xy,
-                                            stream);
-      case 10:  // factors staged with an L2 evict-first policy
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
-                               false, true>(op, lambda, mu, x, y, ncomp, dot_xy,
-                                            stream);
-      case 11:  // both
-        return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
-                               true, true>(op, lambda, mu, x, y, ncomp, dot_xy,
-                                           stream);
       default:
         break;
     }

@@ -9,10 +9,11 @@ generic kernel (variant 1) on the same mesh.
   python tools/bench_apply.py --dim 3 --orders 7 --ne 24 --variants 0,2
 
 Variants (`sfem_op_set_variant`): 0 default, 1 generic kernel, 2 v1 kernels;
-with a library built with `make EXTRA=-DSFEM_EXPERIMENTS` (3-D fp64 Laplacian,
-N = 5..9): 3/4/5 elements per CTA +1/-1/x2, 6/7 resident CTAs +1/-1, 8 factors
-streamed instead of staged, 9 connectivity fetched two steps ahead, 10 factors
-staged with an L2 evict-first policy, 11 = 9 + 10.
+with a library built with `make EXTRA=-DSFEM_EXPERIMENTS`: 3-D Laplacian, any
+order and precision: 9 connectivity fetched two steps ahead, 10 factors staged
+with an L2 evict-first policy, 11 = 9 + 10; 3-D fp64 Laplacian, N = 5..9 only:
+3/4/5 elements per CTA +1/-1/x2, 6/7 resident CTAs +1/-1, 8 factors streamed
+instead of staged.
 """
 
 from __future__ import annotations
