@@ -260,6 +260,8 @@ def run_ours(args):
   quad = Quadrature1D.create_from_nodes_1d(grid1d)
   # Only the fused operator is needed: no invjacs / jacdets / quad_coords.
   op = FusedOperator(mesh, quad, dirichlet_mask=blk.dirichlet, with_mass=False)
+  if int(os.environ.get('SFEM_VARIANT', '0')):  # developer: tuning variants
+    op.set_variant(int(os.environ['SFEM_VARIANT']))
   halo, halo_path = None, None
   if world > 1:
     gathered = [None] * world

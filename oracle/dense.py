@@ -198,13 +198,23 @@ class FESpace:
   """FiniteElementSpace.create restated (fespace.py:306-348)."""
 
   def __init__(self, node_coords, elements, grid_n, grid_type, quad_n,
-               quad_type):
-    self.node_coords = np.asarray(node_coords)
+               quad_type, dtype=np.float64):
+    """`dtype=np.float32` evaluates the SAME dense algorithm in single
+    precision throughout (what the reference does with x64 disabled: the host
+    tables are built in float64 and cast, every einsum / inv / det runs in
+    float32); used to put the fp32 CUDA path's error next to the reference
+    algorithm's own fp32 rounding."""
+    self.dtype = np.dtype(dtype)
+    self.node_coords = np.asarray(node_coords).astype(self.dtype)
     self.elements = np.asarray(elements)
     self.ndim = self.node_coords.shape[-1]
     self.num_nodes = self.node_coords.shape[0]
     self.interp = Interp(self.ndim, grid_n, grid_type, quad_n, quad_type)
     self.quad_weights = weights_nd(weights_1d(quad_n, quad_type), self.ndim)
+    if self.dtype != np.float64:
+      self.interp.matrix = self.interp.matrix.astype(self.dtype)
+      self.interp.matrix_grad = self.interp.matrix_grad.astype(self.dtype)
+      self.quad_weights = self.quad_weights.astype(self.dtype)
     # mesh.py:170-172
     elem_coords = np.stack(
         [gather(self.node_coords[:, k], self.elements)

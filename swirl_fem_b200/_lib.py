@@ -17,7 +17,10 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libswirl_b200.so')
+# SFEM_LIB: an alternative build of the SAME library (e.g. the tuning-variant
+# build `make OUTDIR=../lib_exp EXTRA=-DSFEM_EXPERIMENTS`); never a fallback.
+LIB_PATH = os.environ.get('SFEM_LIB') or os.path.join(_HERE, 'lib',
+                                                      'libswirl_b200.so')
 CSRC_DIR = os.path.join(_HERE, 'csrc')
 
 SFEM_F32, SFEM_F64 = 0, 1

@@ -40,6 +40,19 @@ def rel_err(a, b):
 TOL = {torch.float64: 1e-12, torch.float32: 1e-5}
 
 
+def fp32_bound(n1d, err_ref32):
+  """North-star fp32 tolerance.  N <= 8 (the order 4-8 target band and below):
+  1e-5, no slack.  Larger N: the fp32 error of ANY evaluation grows with the
+  O(N^2) derivative entries, so the CUDA path must be no worse than twice the
+  reference ALGORITHM's own fp32 rounding (`oracle.dense` evaluated in
+  float32 against the float64 oracle), and never looser than that."""
+  return 1e-5 if n1d <= 8 else max(1e-5, 2.0 * err_ref32)
+
+
+def _np_dtype(dtype):
+  return np.float64 if dtype == torch.float64 else np.float32
+
+
 # ----------------------------------------------------------------------------
 # gather / scatter / exchange
 # ----------------------------------------------------------------------------
@@ -156,8 +169,10 @@ def test_fespace_matches_reference(name, dtype):
   from swirl_fem_b200.examples import poisson
   g = load_golden('operator')
   p = name + '/'
-  tol = TOL[dtype] * (10 if dtype == torch.float32 else 1)
   mesh, space = _space_from_golden(g, p, dtype)
+  n1d = int(g[p + 'meta'][2])
+  assert dtype == torch.float64 or n1d <= 8  # every golden case: plain 1e-5
+  tol = TOL[dtype]
   ndim = mesh.ndim
   assert rel_err(space.invjacs.cpu(), g[p + 'invjacs']) < tol
   assert rel_err(space.jacdets.cpu(), g[p + 'jacdets']) < tol
@@ -172,9 +187,10 @@ def test_fespace_matches_reference(name, dtype):
   assert rel_err(uf._evaluate().cpu(), g[p + 'eval_u']) < tol
   assert rel_err(fs.grad(uf)._evaluate().cpu(), g[p + 'eval_grad_u']) < tol
   assert abs(float(space.integrate(uf)) - float(g[p + 'integral_u'])) < (
-      tol * 10)
+      tol * max(1.0, float(np.abs(g[p + 'eval_u']).sum())))
   assert abs(float(space.integrate(lambda x: 1.0)) -
-             float(g[p + 'integral_one'])) < tol * 10
+             float(g[p + 'integral_one'])) < tol * max(
+                 1.0, abs(float(g[p + 'integral_one'])))
   got = space.local_covector(poisson.mass_form, (uf, vf))
   assert rel_err(got.cpu(), g[p + 'mass_local']) < tol
   got = space.local_covector(poisson.stiffness_form, (uf, vf))
@@ -334,12 +350,23 @@ def test_operator_apply_matches_oracle(case, dtype):
   u = rng.standard_normal(mesh.num_nodes)
   interior = 1.0 - bmask
   op = space.operator(dirichlet_mask=bmask, with_mass=True)
-  tol = TOL[dtype] * (20 if dtype == torch.float32 else 1)
+  tol = TOL[dtype]
+  oracle32 = None
+  if dtype == torch.float32 and n1d > 8:
+    oracle32 = dense.FESpace(refined.node_coords, refined.elements, n1d,
+                             helpers.TNAME[GLL], q1d, helpers.TNAME[qt],
+                             dtype=np.float32)
   # 0: default specialised kernels (three-/two-mapping, bulk-async staging),
   # 1: generic runtime-(N, Q) kernel, 2: v1 specialised kernels
   variants = [0, 1, 2] if qt == GLL and q1d == n1d and ndim > 1 else [0]
   for lam, mu in ((0.0, 1.0), (1.0, 0.0), (1833.3, 0.7)):
     want = oracle.apply(u, lam=lam, mu=mu, interior_mask=interior)
+    if oracle32 is not None:
+      ref32 = oracle32.apply(u.astype(np.float32), lam=np.float32(lam),
+                             mu=np.float32(mu),
+                             interior_mask=interior.astype(np.float32))
+      assert ref32.dtype == np.float32
+      tol = fp32_bound(n1d, rel_err(ref32, want))
     for variant in variants:
       op.set_variant(variant)
       dot = torch.zeros((), dtype=torch.float64, device='cuda')
@@ -621,15 +648,18 @@ def test_peer_memory_halo_single_process(case, dtype):
     us.append(torch.as_tensor(field(x0)).to(device=device, dtype=dtype))
     ys.append(torch.empty_like(us[-1]))
     dots.append(torch.zeros((), dtype=torch.float64, device=device))
+  # the checker is the CPU oracle on the UNPARTITIONED mesh (fp64), not
+  # another run of the kernel under test
   ref = refine_premesh(unit_cube_mesh(ne, ndim=ndim, a=-1., b=1.), grid1d)
-  gmesh = Mesh.create(bench_deform(ref.node_coords), ref.elements,
-                      gridpoints_1d=grid1d, device=device, dtype=dtype)
   bmask = ref.finalize_host()['physical_masks']['boundary']
-  gop = FusedOperator(gmesh, quad, dirichlet_mask=bmask, with_mass=True)
-  gu = torch.as_tensor(field(ref.node_coords)).to(device=device, dtype=dtype)
-  tol = 1e-12 if dtype == torch.float64 else 2e-5
+  oracle = dense.FESpace(bench_deform(ref.node_coords), ref.elements, n1d,
+                         helpers.TNAME[GLL], n1d, helpers.TNAME[GLL])
+  gu = field(ref.node_coords)
+  if dtype == torch.float32:
+    gu = gu.astype(np.float32).astype(np.float64)
+  tol = TOL[dtype]
   for epoch, (lam, mu) in enumerate([(0.3, 1.0), (0.0, 1.0), (1.0, 0.5)]):
-    gy = gop.apply(gu, lam=lam, mu=mu).cpu().numpy()
+    gy = oracle.apply(gu, lam=lam, mu=mu, interior_mask=1.0 - bmask)
     # every rank's apply + push first (a push never waits), then the waits
     for r in range(world):
       ops[r].apply_partitioned(us[r], ys[r], plans[r],
@@ -645,10 +675,9 @@ def test_peer_memory_halo_single_process(case, dtype):
       err = np.abs(ys[r].cpu().numpy() - gy[l2g]).max() / np.abs(gy).max()
       assert err < tol, (epoch, r, err)
       total_dot += float(dots[r])
-    want_dot = float((gu.double() * torch.as_tensor(gy).to(device).double()
-                      ).sum())
+    want_dot = float(gu @ gy)
     assert abs(total_dot - want_dot) <= (1e-11 if dtype == torch.float64
-                                         else 1e-4) * abs(want_dot)
+                                         else 1e-5) * np.abs(gu * gy).sum()
   # exchange_ of a plain vector through the same handles (push + wait):
   # multiplicity of every dof = number of ranks holding it
   ones = [torch.ones_like(u) for u in us]

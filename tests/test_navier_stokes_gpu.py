@@ -311,10 +311,6 @@ def test_fixed_form_kernels_equal_the_general_form_path():
     assert rel_err(fast, general.cpu().numpy()) < 1e-13
 
 
-@pytest.mark.skipif(
-    os.environ.get('SFEM_RUN_UNVALIDATED') != '1',
-    reason='written after the round-1 GPU budget was spent; first GPU run is '
-           'due in round 2 (set SFEM_RUN_UNVALIDATED=1)')
 def test_kolmogorov_steps_match_oracle():
   """`examples/kolmogorov.solve_one_step` (niles/datagen/datagen.py:88-102)
   against the oracle over two steps on the doubly periodic square."""
