@@ -56,6 +56,7 @@ def parse_args():
   ap.add_argument('--cg-iters', type=int, default=50)
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-e2e', action='store_true')
+  ap.add_argument('--no-parity', action='store_true')
   return ap.parse_args()
 
 
@@ -220,6 +221,126 @@ def config_name(args):
 
 
 # ----------------------------------------------------------------------------
+# Parity of the measured path against the CPU oracle (outside every timed region)
+# ----------------------------------------------------------------------------
+
+
+def parity_block(rank, world, device, ndim=3, ne=4, order=7, cg_iters=20):
+  """The partitioned apply and CG of THIS job -- real ranks, CUDA-IPC peer
+  memory halo pushed from inside the apply kernel, scalars all-reduced inside
+  the fused step kernel -- on a small mesh of the benchmark's shape, compared
+  on rank 0 with `oracle.dense` on the UNPARTITIONED mesh (the parity target
+  of SURVEY section 8e; reference: gather_scatter.py:246-248, cg.py:75-86).
+  The oracle is the checker here, never the thing measured."""
+  import torch
+  import torch.distributed as dist
+  from swirl_fem_b200.communication import partition as part
+  from swirl_fem_b200.communication.dist_cg import distributed_cg
+  from swirl_fem_b200.core.interpolation import Nodes1D, NodeType, Quadrature1D
+  from swirl_fem_b200.core.mesh import Mesh
+  from swirl_fem_b200.core.operator import FusedOperator
+
+  gll = NodeType.GAUSS_LOBATTO_LEGENDRE
+  grid1d = Nodes1D.create(order + 1, gll)
+  quad = Quadrature1D.create_from_nodes_1d(grid1d)
+  blk = part.block_partition(ne, ndim, grid1d, rank, world)
+  x0 = blk.premesh.node_coords  # undeformed: identifies the global dof
+  mesh = Mesh.create(deform(x0), blk.premesh.elements, gridpoints_1d=grid1d,
+                     device=device, dtype=torch.float64)
+  op = FusedOperator(mesh, quad, dirichlet_mask=blk.dirichlet, with_mass=True)
+  halo, path = None, 'single rank'
+  if world > 1:
+    gathered = [None] * world
+    dist.all_gather_object(gathered, np.sort(blk.interface_global))
+    halo = part.halo_plan_from_interfaces(
+        rank, blk.interface_local, blk.interface_global, gathered,
+        mesh.num_nodes)
+    if os.environ.get('SFEM_HALO', 'p2p') == 'p2p' and halo.enable_p2p(
+        torch.float64, device):
+      path = 'peer memory'
+    else:
+      path = 'nccl all_to_all'
+  field = lambda c: (np.cos(1.3 * c[:, 0]) * (1.0 + 0.5 * c[:, -1]) +  # noqa: E731
+                     0.2 * c[:, 1] ** 2)
+  u = torch.as_tensor(field(x0)).to(device)
+  y = torch.empty_like(u)
+  dot = torch.zeros((), dtype=torch.float64, device=device)
+  for _ in range(3):  # both epoch parities
+    op.apply_partitioned(u, y, halo, blk.num_interface_elements, lam=0.3,
+                         mu=1.0, dot_out=dot)
+  ones = torch.ones_like(u)
+  b_loc = op.apply(ones, lam=1.0, mu=0.0)
+  diag = op.diag()
+  if halo is not None:
+    halo.exchange_(b_loc)
+    halo.exchange_(diag)
+  minv = torch.where(diag != 0, 1.0 / diag, torch.zeros_like(diag))
+  kw = dict(minv=minv, check_every=7,
+            num_interface_elements=blk.num_interface_elements)
+  xs, info_fixed = distributed_cg(op, halo, b_loc, tol=0.0, maxiter=cg_iters,
+                                  **kw)
+  xc, info_conv = distributed_cg(op, halo, b_loc, tol=1e-6, **kw)
+  torch.cuda.synchronize()
+  mine = (x0, y.cpu().numpy(), float(dot), xs.cpu().numpy(), xc.cpu().numpy())
+  if world > 1:
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0)
+    halo.disable_p2p()
+  else:
+    parts = [mine]
+  if rank != 0:
+    return None
+
+  from oracle import dense
+  from swirl_fem_b200.common.premesh_commons import unit_cube_mesh
+  from swirl_fem_b200.core.mesh_refiner import refine_premesh
+  ref = refine_premesh(unit_cube_mesh(ne, ndim=ndim, a=-1., b=1.), grid1d)
+  bmask = ref.finalize_host()['physical_masks']['boundary']
+  interior = 1.0 - bmask
+  fes = dense.FESpace(deform(ref.node_coords), ref.elements, order + 1,
+                      'gauss_lobatto_legendre', order + 1,
+                      'gauss_lobatto_legendre')
+  gu = field(ref.node_coords)
+  gy = fes.apply(gu, lam=0.3, mu=1.0, interior_mask=interior)
+  gb = fes.apply(np.ones(ref.num_nodes), 1.0, 0.0, interior)
+  gd = fes.stiffness_diag(interior)
+  gminv = np.where(gd != 0, 1.0 / np.where(gd != 0, gd, 1.0), 0.0)
+  A = lambda v: fes.apply(v, interior_mask=interior)  # noqa: E731
+  gx, _ = dense.cg(A, gb, tol=0.0, maxiter=cg_iters, M=lambda r: gminv * r)
+  gxc, ginfo = dense.cg(A, gb, tol=1e-6, M=lambda r: gminv * r)
+  key = lambda c: np.round(np.asarray(c) * 1e9).astype(np.int64)  # noqa: E731
+  gk = key(ref.node_coords)
+  order_ = np.lexsort(gk.T[::-1])
+  rec = [('', np.int64)] * ndim
+  view_g = np.ascontiguousarray(gk[order_]).view(rec).ravel()
+  apply_err = x_err = xc_err = 0.0
+  total_dot = 0.0
+  for c, yv, dv, xv, xcv in parts:
+    view_l = np.ascontiguousarray(key(c)).view(rec).ravel()
+    l2g = order_[np.searchsorted(view_g, view_l)]
+    assert np.array_equal(gk[l2g], key(c))
+    apply_err = max(apply_err, np.abs(yv - gy[l2g]).max() / np.abs(gy).max())
+    x_err = max(x_err, np.abs(xv - gx[l2g]).max() / np.abs(gx).max())
+    xc_err = max(xc_err, np.abs(xcv - gxc[l2g]).max() / np.abs(gxc).max())
+    total_dot += dv
+  return {
+      'mesh': f'{ndim}-D ne={ne} order {order}, {ref.num_nodes} dofs, '
+              f'{world} rank(s), halo: {path}',
+      'checker': 'oracle.dense (numpy restatement of the reference, fp64) on '
+                 'the unpartitioned mesh, rank 0',
+      'rel_err': float(apply_err),
+      'apply_dot_rel_err': float(abs(total_dot - gu @ gy) / abs(gu @ gy)),
+      'cg_fixed_iterations': int(info_fixed['num_iterations']),
+      'cg_x_rel_err_after_fixed_iterations': float(x_err),
+      'cg_iterations': int(info_conv['num_iterations']),
+      'cg_iterations_oracle': int(ginfo['num_iterations']),
+      'cg_solution_rel_err': float(xc_err),
+      'ok': bool(apply_err <= 1e-12 and x_err <= 1e-9 and abs(
+          info_conv['num_iterations'] - ginfo['num_iterations']) <= 1),
+  }
+
+
+# ----------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------
 
@@ -251,6 +372,11 @@ def run_ours(args):
   esz = 8 if args.dtype == 'f64' else 4
   gll = NodeType.GAUSS_LOBATTO_LEGENDRE
   grid1d = Nodes1D.create(args.order + 1, gll)
+
+  # parity of this job's path (same ranks, same halo) before anything is timed
+  parity = None
+  if not args.no_parity:
+    parity = parity_block(rank, world, device, ndim=args.dim, order=args.order)
 
   t_setup = time.perf_counter()
   blk = part.block_partition(args.ne, args.dim, grid1d, rank, world)
@@ -493,6 +619,7 @@ def run_ours(args):
         'roofline': roofline,
         'cpu_baseline': cpu,
         'cg': cg_info,
+        'parity': parity,
     }
     print(json.dumps(line), flush=True)
   if world > 1:

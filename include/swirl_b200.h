@@ -368,7 +368,7 @@ int sfem_scalar_exchange_timed_out(const sfem_scalar_exchange* h,
 typedef struct {
   double tol;          /* relative tolerance (default 1e-5)                  */
   double atol;         /* absolute tolerance                                 */
-  int64_t maxiter;     /* <= 0: 10 * size                                    */
+  int64_t maxiter;     /* < 0: 10 * size (0 = no iteration, as cg.py:68-73)   */
   int32_t precond;     /* 0: identity, 1: Jacobi (minv = 1/diag, 0 on mask)  */
   int32_t check_every; /* host polls the device flag every k iterations      */
   double lambda, mu;   /* operator coefficients                              */
@@ -415,7 +415,23 @@ int sfem_cg_update(int dtype, int64_t n, void* x, void* r, const void* p,
 int sfem_cg_direction(int dtype, int64_t n, const void* r, void* p,
                       const void* minv, void* state, sfem_stream_t stream);
 int sfem_cg_advance(void* state, sfem_stream_t stream);
-/* Copies the state to the host (synchronises the stream). */
+/* `iters` whole iterations of the body of swirl_fem/linalg/cg.py:75-86 with
+ * TWO (single GPU) or THREE (partitioned) launches each: the operator apply
+ * p -> Ap with p.Ap in its epilogue (halo != NULL: sfem_op_apply_halo +
+ * sfem_halo_wait_unpack), then ONE co-resident kernel that does update,
+ * direction, both dot-product reductions, the scalar advance of
+ * sfem_cg_advance and the zero fill of the next apply.  Partitioned: `sx`
+ * all-reduces the two scalars over peer memory INSIDE that kernel (no NCCL
+ * call in the iteration; NULL only with halo == NULL).  Kernels are no-ops once
+ * the state's flag is set; a peer that never answers sets done = 2. */
+int sfem_cg_iterate(const sfem_op* op, sfem_halo* halo,
+                    sfem_scalar_exchange* sx, double lambda, double mu,
+                    int64_t num_interface_elements, int32_t ncomp, void* x,
+                    void* r, void* p, void* Ap, const void* minv,
+                    const uint8_t* owned, void* state, int32_t iters,
+                    sfem_stream_t stream);
+/* Copies the state to the host (synchronises the stream).  *done: 0 running,
+ * 1 converged or maxiter reached, 2 a peer-memory wait timed out (fatal). */
 int sfem_cg_read(const void* state, sfem_cg_info* info, int32_t* done,
                  sfem_stream_t stream);
 

@@ -142,11 +142,12 @@ class Interp:
     """interpolation.py:254-263, vmapped over elements: (E, n) -> (E, q)."""
     if self.collocated:
       return x_local
-    return np.einsum('ij,ej->ei', self.matrix, x_local)
+    return np.einsum('ij,ej->ei', self.matrix, x_local, optimize=True)
 
   def interpolate_grad(self, x_local: np.ndarray) -> np.ndarray:
     """interpolation.py:288-292, vmapped over elements: (E, n) -> (E, q, d)."""
-    return np.einsum('qnd,en->eqd', self.matrix_grad, x_local)
+    return np.einsum('qnd,en->eqd', self.matrix_grad, x_local,
+                     optimize=True)  # same contraction, routed through BLAS
 
 
 # ----------------------------------------------------------------------------
@@ -269,7 +270,8 @@ class FESpace:
     gu = self.eval_scalar_grad(u_local)                       # (E,q,d) physical
     wq = gu * (self.jacdets * self.quad_weights)[..., None]   # (E,q,d)
     ref = np.einsum('mqj,mqji->mqi', wq, self.invjacs)        # back to reference
-    return np.einsum('qni,mqi->mn', self.interp.matrix_grad, ref)
+    return np.einsum('qni,mqi->mn', self.interp.matrix_grad, ref,
+                     optimize=True)
 
   def helmholtz_local(self, u_local, lam, mu):
     out = 0.

@@ -161,6 +161,10 @@ SIGNATURES = {
     'sfem_cg_direction': (ctypes.c_int, [ctypes.c_int, _c_i64, _c_ptr, _c_ptr,
                                          _c_ptr, _c_ptr, _c_ptr]),
     'sfem_cg_advance': (ctypes.c_int, [_c_ptr, _c_ptr]),
+    'sfem_cg_iterate': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr, _c_f64, _c_f64,
+                                       _c_i64, _c_i32, _c_ptr, _c_ptr, _c_ptr,
+                                       _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i32,
+                                       _c_ptr]),
     'sfem_cg_read': (ctypes.c_int, [_c_ptr, ctypes.POINTER(CgInfo),
                                     ctypes.POINTER(_c_i32), _c_ptr]),
     'sfem_axpby': (ctypes.c_int, [ctypes.c_int, _c_i64, _c_f64, _c_ptr, _c_f64,

@@ -1,22 +1,30 @@
-"""Element-partitioned (P)CG: one process per GPU, NCCL for the two scalars.
+"""Element-partitioned (P)CG: one process per GPU.
 
-Same recurrence and stopping rule as `swirl_fem/linalg/cg.py:54-97`, executed
-by the fused CUDA building blocks (`sfem_cg_init/_update/_direction/_advance`)
-on a device-resident state.  Per iteration and rank:
+Same recurrence and stopping rule as `swirl_fem/linalg/cg.py:54-97` on a
+device-resident state.  Default path (peer-memory halo + `ScalarExchange`),
+THREE launches per iteration and rank, no NCCL call (`sfem_cg_iterate`):
 
-  apply (local block, p.Ap partial in the kernel epilogue)
-  -> halo exchange of Ap (pack, NCCL send/recv over NVLink, unpack-add)
-  -> all-reduce of p.Ap          (1 double; element-wise partial sums need no
-                                  ownership weights)
-  -> update kernel (x, r, partial r.z over OWNED dofs)
-  -> all-reduce of r.z           (1 double)
-  -> direction kernel, scalar advance (device side)
+  apply kernel     local block, interface elements first, shared dofs pushed
+                   to the peers over NVLink from inside the kernel, canonical
+                   sum hidden under the interior elements, partial p.Ap in the
+                   epilogue (element-wise partial sums need no ownership
+                   weights)
+  wait kernel      whatever is left of the exchange (normally nothing)
+  step kernel      all-reduce of p.Ap over peer memory (warp 0 of CTA 0),
+                   x, r update with partial r.z over the OWNED dofs, grid
+                   arrival, all-reduce of r.z (last CTA), scalar advance +
+                   convergence flag, direction update, zero fill of the next
+                   apply's shared-dof prefix
+
+Fallback (`SFEM_HALO=nccl`, or peer mapping unavailable): the building blocks
+`sfem_cg_update/_direction/_advance` with two NCCL all-reduces in between.
 
 There is no host synchronisation inside the loop: the convergence flag is read
 every `check_every` iterations (it is identical on all ranks because it is
-computed from all-reduced scalars).  The reference has no distributed CG; its
-hook is `dot_fn` (`cg.py:26-31`), and the parity target is the unpartitioned
-solve on the same global mesh.
+computed from all-reduced scalars).  A peer-memory wait that times out is
+FATAL (`SwirlB200Error` at the next read).  The reference has no distributed
+CG; its hook is `dot_fn` (`cg.py:26-31`), and the parity target is the
+unpartitioned solve on the same global mesh.
 """
 
 from __future__ import annotations
@@ -43,9 +51,10 @@ def distributed_cg(op, halo, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None,
       diagonal before inverting), or None.
     maxiter: default 10 * (global number of dofs).
     scalar_exchange: a `communication.scalar_exchange.ScalarExchange`: the two
-      dot products per iteration are all-reduced over peer memory by one
-      single-CTA kernel each instead of an NCCL call (sums in rank order,
-      bitwise identical on all ranks).  None: NCCL.
+      dot products per iteration are all-reduced over peer memory inside the
+      fused step kernel (sums in rank order, bitwise identical on all ranks).
+      None: one is created (and cached on `halo`) when the halo runs over peer
+      memory; NCCL otherwise.
   Returns:
     `(x, {'residual', 'num_iterations'})` as `linalg.cg.cg`.
   """
@@ -77,6 +86,27 @@ def distributed_cg(op, halo, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None,
       dist.all_reduce(total, group=group)
     maxiter = 10 * int(total.item())
   stream = _lib.stream_ptr(dev)
+  p2p = halo is not None and halo.p2p_handle(b) is not None
+  if p2p and world > 1:
+    # ranks may arrive seconds apart (set-up, first-use module loading): the
+    # bounded device-side waits must only ever see communication time
+    dist.barrier(group=group)
+    if scalar_exchange is None:
+      scalar_exchange = halo.scalar_exchange(dev, group)
+  single = halo is None or not halo.peers
+  fused = single or (p2p and scalar_exchange is not None
+                     and scalar_exchange.world > 1
+                     and num_interface_elements is not None)
+
+  def check_timeouts():
+    if p2p and halo.p2p_timed_out(dev):
+      raise _lib.SwirlB200Error(
+          'halo exchange: a peer never raised its flag (4 s device-side '
+          'timeout); the result is invalid')
+    if scalar_exchange is not None and scalar_exchange.timed_out():
+      raise _lib.SwirlB200Error(
+          'scalar all-reduce: a peer never answered (4 s device-side '
+          'timeout); the result is invalid')
 
   def apply(src, dot_out):
     if halo is not None and num_interface_elements is not None:
@@ -89,7 +119,7 @@ def distributed_cg(op, halo, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None,
       halo.exchange_(ap)
 
   def allreduce(view):
-    if world > 1:
+    if not single:
       if scalar_exchange is not None:
         scalar_exchange.allreduce_(view)
       else:
@@ -108,12 +138,26 @@ def distributed_cg(op, halo, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None,
     done = ctypes.c_int32(0)
     pap = state[0:1]
     gnew = state[1:2]
+    hp = None if single else halo.p2p_handle(b)
+    sxh = None if single else scalar_exchange.handle
     while True:
       _lib._check(lib.sfem_cg_read(_lib.ptr(state), ctypes.byref(info),
                                    ctypes.byref(done), stream), 'sfem_cg_read')
+      check_timeouts()
+      if done.value == 2:
+        raise _lib.SwirlB200Error('distributed CG: a peer-memory wait timed '
+                                  'out inside the step kernel')
       if done.value:
         break
-      for _ in range(check_every):
+      iters = int(min(check_every, max(1, maxiter - info.num_iterations)))
+      if fused:
+        _lib._check(lib.sfem_cg_iterate(
+            op.handle, hp, sxh, float(lam), float(mu),
+            int(num_interface_elements or 0), 1, _lib.ptr(x), _lib.ptr(r),
+            _lib.ptr(p), _lib.ptr(ap), _lib.ptr(minv), _lib.ptr(owned),
+            _lib.ptr(state), iters, stream), 'sfem_cg_iterate')
+        continue
+      for _ in range(iters):
         apply(p, pap)
         allreduce(pap)
         _lib._check(lib.sfem_cg_update(

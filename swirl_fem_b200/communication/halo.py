@@ -335,6 +335,15 @@ class HaloPlan:
       lib.sfem_ipc_free(p['region'])
     self._p2p = None
 
+  def scalar_exchange(self, device, group=None):
+    """The `ScalarExchange` of this partition (collective on first use; None
+    if peer mapping is unavailable).  Cached: CG solves reuse it."""
+    key = ('sx', str(device))
+    if key not in self._dev:
+      from swirl_fem_b200.communication.scalar_exchange import ScalarExchange  # pylint: disable=g-import-not-at-top
+      self._dev[key] = ScalarExchange.create(device, group=group)
+    return self._dev[key]
+
   def p2p_handle(self, u: torch.Tensor):
     p = getattr(self, '_p2p', None)
     if p is None or p['dtype'] != u.dtype or u.dim() != 1:

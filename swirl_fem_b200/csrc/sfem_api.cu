@@ -121,9 +121,11 @@ static int apply_dispatch(const sfem_op& op, double lambda, double mu,
 }
 
 // shared by sfem_op_apply and the CG driver
+// `prezeroed`: y[0 .. n_zero) and *dot_xy are already zero (fused CG loop: the
+// previous cg_step_kernel did it), so no fill is enqueued.
 int op_apply_internal(const sfem_op* op, double lambda, double mu,
                       const void* x, void* y, int ncomp, double* dot_xy,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, bool prezeroed = false) {
   const sfem_space_desc& d = op->base.desc;
   SFEM_REQUIRE(lambda == 0.0 || op->with_mass,
                "operator was created without mass factors (with_mass = 0) but "
@@ -134,7 +136,9 @@ int op_apply_internal(const sfem_op* op, double lambda, double mu,
   const bool pdl = op->variant == 0 && d.collocated && d.dim == 3 &&
                    d.n1d <= 16 && (op->n_zero > 0 || dot_xy);
   sfem_op sub = *op;
-  if (pdl) {
+  if (prezeroed) {
+    sub.pdl = false;
+  } else if (pdl) {
     int rc = launch_zero_fill(y, esz * (size_t)op->n_zero * ncomp, dot_xy,
                               stream, &sub.pdl);
     if (rc) return rc;

@@ -288,6 +288,85 @@ __device__ __forceinline__ void halo_unpack_slices(const HaloDev& h, T* y,
   }
 }
 
+// ---- peer-memory all-reduce of a few doubles (the CG scalars) ------------------
+// Region of a rank: [parity 2][source rank `world`] slots of 64 bytes.
+struct ScalarSlot {
+  double v[4];
+  uint64_t epoch;
+  uint64_t pad[3];
+};
+static_assert(sizeof(ScalarSlot) == 64, "slot size");
+
+// Device view of a `sfem_scalar_exchange` handle (world == 0: no exchange).
+struct ScalarDev {
+  int rank;
+  int world;
+  char* my_region;
+  const uint64_t* peer_regions;  // device array (world) of region addresses
+  unsigned* timed_out;
+};
+
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p,
+                                               unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu64(
+    const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// All-reduce (sum) of `count` <= 4 doubles by ONE WARP (all 32 lanes call it;
+// `mine` must hold the same values on every lane).  Lane t publishes this
+// rank's values into rank t's region and raises the epoch there, then waits
+// (bounded: ~4 s of globaltimer) for rank t's epoch in the local region; every
+// lane then adds the ranks' values in ascending rank order, so the result is
+// bitwise identical on every lane and every rank.  Returns false on a timeout
+// (the sticky flag is set; the sums are then meaningless).
+__device__ __forceinline__ bool scalar_allreduce_warp(const ScalarDev& sx,
+                                                      uint64_t epoch,
+                                                      double (&vals)[4],
+                                                      int count) {
+  const unsigned parity = (unsigned)(epoch & 1u);
+  const int lane = threadIdx.x & 31;
+  bool ok = true;
+  for (int t = lane; t < sx.world; t += 32) {
+    ScalarSlot* dst = reinterpret_cast<ScalarSlot*>(sx.peer_regions[t]) +
+                      (parity * sx.world + sx.rank);
+    for (int k = 0; k < count; ++k) dst->v[k] = vals[k];
+    __threadfence_system();
+    st_release_sys(&dst->epoch, epoch);
+  }
+  for (int t = lane; t < sx.world; t += 32) {
+    const ScalarSlot* src = reinterpret_cast<const ScalarSlot*>(sx.my_region) +
+                            (parity * sx.world + t);
+    uint64_t t0 = 0;
+    unsigned spins = 0;
+    while (ld_acquire_sys(&src->epoch) < epoch) {
+      if ((++spins & 1023u) == 0) {
+        uint64_t now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 4000000000ull) {
+          atomicExch(sx.timed_out, 1u);
+          ok = false;
+          break;
+        }
+      }
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  const ScalarSlot* base =
+      reinterpret_cast<const ScalarSlot*>(sx.my_region) + parity * sx.world;
+  for (int k = 0; k < count; ++k) {
+    double acc = 0.0;
+    for (int t = 0; t < sx.world; ++t) acc += __ldcg(&base[t].v[k]);
+    vals[k] = acc;
+  }
+  return ok;
+}
+
 // symmetric index of (i,k), i<=k, in the packed d(d+1)/2 layout
 __host__ __device__ constexpr int sym_index(int dim, int i, int k) {
   return dim == 1 ? 0
@@ -349,9 +428,32 @@ struct sfem_op {
   // connectivity, gather, first bulk copy -- overlaps the zero fill; it waits
   // with griddepcontrol.wait before its first write to y)
   bool pdl = false;
+  // set on a shallow copy by the fused CG loop: y[0 .. n_zero) and the dot
+  // accumulator were already zeroed by the previous cg_step_kernel
+  bool prezeroed = false;
+};
+
+// Peer-memory all-reduce handle (sfem_halo.cu).
+struct sfem_scalar_exchange {
+  int rank = 0, world = 0;
+  char* my_region = nullptr;
+  uint64_t* d_peer_regions = nullptr;  // device (world) addresses
+  unsigned* d_timeout = nullptr;
+  uint64_t epoch = 0;
 };
 
 namespace sfem {
+inline ScalarDev scalar_view(const sfem_scalar_exchange* h) {
+  ScalarDev d{};
+  if (h) {
+    d.rank = h->rank;
+    d.world = h->world;
+    d.my_region = h->my_region;
+    d.peer_regions = h->d_peer_regions;
+    d.timed_out = h->d_timeout;
+  }
+  return d;
+}
 // Zero fill of y's shared-dof prefix and of the dot accumulator by ONE small
 // kernel (one CTA per SM) that lets its dependents launch at once.
 // `*used_kernel` = false when y is not 16-byte aligned and plain memsets were

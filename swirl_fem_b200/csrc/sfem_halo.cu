@@ -30,73 +30,19 @@ struct sfem_halo {
   int fuse_unpack = 1;
 };
 
-// Peer-memory all-reduce of a few doubles (the CG scalars).  Region of a rank:
-// [parity 2][source rank `world`] slots of 64 bytes {double v[4]; uint64 epoch}.
-struct sfem_scalar_exchange {
-  int rank = 0, world = 0;
-  char* my_region = nullptr;
-  uint64_t* d_peer_regions = nullptr;  // device (world) addresses
-  unsigned* d_timeout = nullptr;
-  uint64_t epoch = 0;
-};
-
 namespace sfem {
 
 namespace {
 
-struct ScalarSlot {
-  double v[4];
-  uint64_t epoch;
-  uint64_t pad[3];
-};
-static_assert(sizeof(ScalarSlot) == 64, "slot size");
-
-// ONE CTA.  Thread t publishes this rank's values into rank t's region (slot
-// of this rank) and raises the epoch there; then thread t waits for rank t's
-// epoch in the local region; thread k sums value k over the ranks in
-// ascending rank order -> bitwise identical results on every rank.
-__global__ void __launch_bounds__(128)
-scalar_allreduce_kernel(double* __restrict__ values, int count, int rank,
-                        int world, char* my_region,
-                        const uint64_t* __restrict__ peer_regions,
-                        uint64_t epoch, unsigned* timed_out) {
+// ONE warp: the all-reduce of sfem_common.cuh as a stand-alone launch.
+__global__ void __launch_bounds__(32)
+scalar_allreduce_kernel(double* __restrict__ values, int count,
+                        const ScalarDev sx, uint64_t epoch) {
   pdl_wait();
-  const unsigned parity = (unsigned)(epoch & 1u);
-  __shared__ double mine[4];
-  if ((int)threadIdx.x < count) mine[threadIdx.x] = values[threadIdx.x];
-  __syncthreads();
-  for (int t = threadIdx.x; t < world; t += blockDim.x) {
-    ScalarSlot* dst = reinterpret_cast<ScalarSlot*>(peer_regions[t]) +
-                      (parity * world + rank);
-    for (int k = 0; k < count; ++k) dst->v[k] = mine[k];
-    __threadfence_system();
-    st_release_sys(&dst->epoch, epoch);
-  }
-  for (int t = threadIdx.x; t < world; t += blockDim.x) {
-    const ScalarSlot* src =
-        reinterpret_cast<const ScalarSlot*>(my_region) + (parity * world + t);
-    uint64_t t0 = 0;
-    unsigned spins = 0;
-    while (ld_acquire_sys(&src->epoch) < epoch) {
-      if ((++spins & 1023u) == 0) {
-        uint64_t now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t0 == 0) t0 = now;
-        if (now - t0 > 4000000000ull) {
-          atomicExch(timed_out, 1u);
-          break;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if ((int)threadIdx.x < count) {
-    const ScalarSlot* base =
-        reinterpret_cast<const ScalarSlot*>(my_region) + parity * world;
-    double acc = 0.0;
-    for (int t = 0; t < world; ++t) acc += __ldcg(&base[t].v[threadIdx.x]);
-    values[threadIdx.x] = acc;
-  }
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int k = 0; k < count; ++k) v[k] = values[k];
+  scalar_allreduce_warp(sx, epoch, v, count);
+  if ((int)threadIdx.x < count) values[threadIdx.x] = v[threadIdx.x];
 }
 
 }  // namespace
@@ -107,7 +53,7 @@ int launch_apply3d_halo(const sfem_op& op, double lambda, double mu,
                         cudaStream_t stream);
 int op_apply_internal(const sfem_op* op, double lambda, double mu,
                       const void* x, void* y, int ncomp, double* dot_xy,
-                      cudaStream_t stream);
+                      cudaStream_t stream, bool prezeroed = false);
 
 namespace {
 
@@ -220,6 +166,66 @@ int push_standalone(sfem_halo* h, const HaloDev& hd, const void* u,
 }  // namespace
 }  // namespace sfem
 
+namespace sfem {
+// One predicate for "the exchange is pushed from inside the apply kernel".
+static bool halo_fused(const sfem_op* op, const sfem_halo* halo) {
+  const sfem_space_desc& d = op->base.desc;
+  return op->variant == 0 && d.collocated && d.dim == 3 && d.n1d >= 2 &&
+         d.n1d <= 16 && d.num_elements > 0 && halo->desc.num_peers < 32;
+}
+
+int op_apply_halo_internal(const sfem_op* op, sfem_halo* halo, double lambda,
+                           double mu, const void* x, void* y,
+                           int64_t num_interface_elements, double* dot_xy,
+                           bool prezeroed, cudaStream_t stream) {
+  sfem_stream_t stream_ = (sfem_stream_t)stream;
+  SFEM_REQUIRE(op && halo && x && y, "null argument");
+  SFEM_REQUIRE(x != y, "sfem_op_apply_halo is out of place");
+  const sfem_space_desc& d = op->base.desc;
+  SFEM_REQUIRE(d.dtype == halo->desc.dtype, "operator / halo dtype mismatch");
+  SFEM_REQUIRE(num_interface_elements >= 0 &&
+                   num_interface_elements <= d.num_elements,
+               "num_interface_elements out of range");
+  SFEM_REQUIRE(lambda == 0.0 || op->with_mass,
+               "operator was created without mass factors but lambda != 0");
+  if (!halo_fused(op, halo)) {
+    int rc = op_apply_internal(op, lambda, mu, x, y, 1, dot_xy, stream,
+                               prezeroed);
+    if (rc) return rc;
+    return sfem_halo_push(halo, y, stream_);
+  }
+  const size_t esz = d.dtype == SFEM_F64 ? 8 : 4;
+  bool pdl = !prezeroed && (op->n_zero > 0 || dot_xy);
+  if (pdl) {
+    int rc = launch_zero_fill(y, esz * (size_t)op->n_zero, dot_xy, stream,
+                              &pdl);
+    if (rc) return rc;
+  }
+  // the epoch advances only once the launch has succeeded: a failed launch
+  // must not shift this rank's parity against its peers
+  const uint64_t epoch0 = halo->epoch;
+  const unsigned uslice0 = halo->cur_uslice;
+  HaloDev hd = begin_epoch(halo, num_interface_elements);
+  sfem_op sub = *op;
+  sub.fuse = &hd;  // the launcher sizes the work items for its grid
+  sub.pdl = pdl;
+  const int rc = d.dtype == SFEM_F64
+                     ? launch_apply3d_halo<double>(sub, lambda, mu, x, y,
+                                                   dot_xy, stream)
+                     : launch_apply3d_halo<float>(sub, lambda, mu, x, y,
+                                                  dot_xy, stream);
+  if (rc) {
+    halo->epoch = epoch0;
+    halo->cur_uslice = uslice0;
+    return rc;
+  }
+  halo->cur_uslice = hd.uslice;
+  return rc;
+}
+
+
+}  // namespace sfem
+
 extern "C" {
 
 int sfem_ipc_alloc(int64_t bytes, void** dev_ptr, void* handle) {
@@ -311,10 +317,8 @@ int sfem_scalar_allreduce(sfem_scalar_exchange* h, double* values,
   SFEM_REQUIRE(count >= 1 && count <= 4, "count must be 1..4");
   h->epoch += 1;
   SFEM_CUDA_CHECK(launch_maybe_pdl(
-      true, scalar_allreduce_kernel, dim3(1), dim3(128), 0,
-      (cudaStream_t)stream, values, (int)count, h->rank, h->world,
-      h->my_region, (const uint64_t*)h->d_peer_regions, h->epoch,
-      h->d_timeout));
+      true, scalar_allreduce_kernel, dim3(1), dim3(32), 0,
+      (cudaStream_t)stream, values, (int)count, scalar_view(h), h->epoch));
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }
@@ -452,44 +456,10 @@ int sfem_halo_debug_times(const sfem_halo* halo, uint64_t* out8,
 int sfem_op_apply_halo(const sfem_op* op, sfem_halo* halo, double lambda,
                        double mu, const void* x, void* y,
                        int64_t num_interface_elements, void* dot_xy,
-                       sfem_stream_t stream_) {
-  using namespace sfem;
-  cudaStream_t stream = (cudaStream_t)stream_;
-  SFEM_REQUIRE(op && halo && x && y, "null argument");
-  SFEM_REQUIRE(x != y, "sfem_op_apply_halo is out of place");
-  const sfem_space_desc& d = op->base.desc;
-  SFEM_REQUIRE(d.dtype == halo->desc.dtype, "operator / halo dtype mismatch");
-  SFEM_REQUIRE(num_interface_elements >= 0 &&
-                   num_interface_elements <= d.num_elements,
-               "num_interface_elements out of range");
-  SFEM_REQUIRE(lambda == 0.0 || op->with_mass,
-               "operator was created without mass factors but lambda != 0");
-  const bool fused = op->variant == 0 && d.collocated && d.dim == 3 &&
-                     d.n1d >= 2 && d.n1d <= 16 && d.num_elements > 0 &&
-                     halo->desc.num_peers < 32;
-  if (!fused) {
-    int rc = op_apply_internal(op, lambda, mu, x, y, 1, (double*)dot_xy, stream);
-    if (rc) return rc;
-    return sfem_halo_push(halo, y, stream_);
-  }
-  const size_t esz = d.dtype == SFEM_F64 ? 8 : 4;
-  bool pdl = op->n_zero > 0 || dot_xy;
-  if (pdl) {
-    int rc = launch_zero_fill(y, esz * (size_t)op->n_zero, (double*)dot_xy,
-                              stream, &pdl);
-    if (rc) return rc;
-  }
-  HaloDev hd = begin_epoch(halo, num_interface_elements);
-  sfem_op sub = *op;
-  sub.fuse = &hd;  // the launcher sizes the work items for its grid
-  sub.pdl = pdl;
-  const int rc = d.dtype == SFEM_F64
-                     ? launch_apply3d_halo<double>(sub, lambda, mu, x, y,
-                                                   (double*)dot_xy, stream)
-                     : launch_apply3d_halo<float>(sub, lambda, mu, x, y,
-                                                  (double*)dot_xy, stream);
-  halo->cur_uslice = hd.uslice;
-  return rc;
+                       sfem_stream_t stream) {
+  return sfem::op_apply_halo_internal(op, halo, lambda, mu, x, y,
+                                      num_interface_elements, (double*)dot_xy,
+                                      false, (cudaStream_t)stream);
 }
 
 }  // extern "C"

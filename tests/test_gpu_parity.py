@@ -725,6 +725,124 @@ def test_peer_memory_scalar_allreduce_single_process(world):
     sx[0].allreduce_(torch.zeros(2, dtype=torch.float32, device=device))
 
 
+@pytest.mark.parametrize('case', [(3, 2, 8, 2), (3, 4, 5, 4), (2, 8, 4, 4)],
+                         ids=lambda c: f'{c[0]}d_ne{c[1]}_N{c[2]}_w{c[3]}')
+def test_fused_distributed_cg_single_process(case):
+  """The partitioned CG loop of `sfem_cg_iterate` -- apply with the in-kernel
+  halo push, wait kernel, ONE step kernel that all-reduces both scalars over
+  peer memory -- with all ranks' blocks on ONE GPU (one stream per rank, the
+  kernels wait for one another on the device), against the oracle's CG on the
+  unpartitioned mesh: iteration count +-1 and the solution."""
+  import ctypes
+  from swirl_fem_b200 import _lib
+  from swirl_fem_b200.common.premesh_commons import unit_cube_mesh
+  from swirl_fem_b200.communication import partition as part
+  from swirl_fem_b200.communication.halo import HaloPlan
+  from swirl_fem_b200.communication.scalar_exchange import ScalarExchange
+  from swirl_fem_b200.core.interpolation import Nodes1D, Quadrature1D
+  from swirl_fem_b200.core.mesh import Mesh
+  from swirl_fem_b200.core.mesh_refiner import refine_premesh
+  from swirl_fem_b200.core.operator import FusedOperator
+  from tests.helpers import local_to_global
+  ndim, ne, n1d, world = case
+  device = torch.device('cuda', 0)
+  dtype = torch.float64
+  lib = _lib.lib()
+  grid1d = Nodes1D.create(n1d, GLL)
+  quad = Quadrature1D.create_from_nodes_1d(grid1d)
+  blks = [part.block_partition(ne, ndim, grid1d, r, world)
+          for r in range(world)]
+  gathered = [np.sort(b.interface_global) for b in blks]
+  plans = [part.halo_plan_from_interfaces(
+      r, b.interface_local, b.interface_global, gathered, b.premesh.num_nodes)
+           for r, b in enumerate(blks)]
+  HaloPlan.enable_p2p_local(plans, dtype, device)
+  sx = ScalarExchange.create_local(world, device)
+  streams = [torch.cuda.Stream(device=device) for _ in range(world)]
+  bench_deform = lambda x: x + 0.08 * np.sin(  # noqa: E731
+      np.pi * x[:, np.roll(np.arange(ndim), 1)]) * (1 - x ** 2)
+  ranks = []
+  for r, b in enumerate(blks):
+    mesh = Mesh.create(bench_deform(b.premesh.node_coords), b.premesh.elements,
+                       gridpoints_1d=grid1d, device=device, dtype=dtype)
+    op = FusedOperator(mesh, quad, dirichlet_mask=b.dirichlet, with_mass=True)
+    rhs = op.apply(torch.ones(mesh.num_nodes, dtype=dtype, device=device),
+                   lam=1.0, mu=0.0)
+    ranks.append(dict(op=op, rhs=rhs, diag=op.diag()))
+  # assemble rhs and diagonal across the ranks (pushes first, then the waits)
+  for name in ('rhs', 'diag'):
+    for r in range(world):
+      plans[r].p2p_push(ranks[r][name])
+    for r in range(world):
+      plans[r].p2p_wait_unpack(ranks[r][name])
+  torch.cuda.synchronize()
+  tol, check_every = 1e-8, 6
+  for r, st in enumerate(ranks):
+    d = st['diag']
+    st['minv'] = torch.where(d != 0, 1.0 / d, torch.zeros_like(d))
+    st['x'] = torch.zeros_like(st['rhs'])
+    st['r'] = torch.empty_like(st['rhs'])
+    st['p'] = torch.empty_like(st['rhs'])
+    st['ap'] = torch.zeros_like(st['rhs'])          # A x0 with x0 = 0
+    st['owned'] = plans[r].owned_mask(device)
+    st['state'] = torch.zeros(int(lib.sfem_cg_state_bytes()) // 8,
+                              dtype=torch.float64, device=device)
+  torch.cuda.synchronize()
+  n_owned = sum(int(pl.owned.sum()) for pl in plans)
+  for r, st in enumerate(ranks):
+    with torch.cuda.stream(streams[r]):
+      _lib._check(lib.sfem_cg_init(
+          _lib.SFEM_F64, st['rhs'].numel(), _lib.ptr(st['rhs']),
+          _lib.ptr(st['ap']), _lib.ptr(st['minv']), _lib.ptr(st['owned']),
+          _lib.ptr(st['r']), _lib.ptr(st['p']), _lib.ptr(st['state']), tol,
+          0.0, 10 * n_owned, streams[r].cuda_stream), 'sfem_cg_init')
+      sx[r].allreduce_(st['state'][2:4])
+      _lib._check(lib.sfem_cg_init_finish(_lib.ptr(st['state']),
+                                          streams[r].cuda_stream),
+                  'sfem_cg_init_finish')
+  infos = [_lib.CgInfo() for _ in range(world)]
+  for _ in range(60):
+    dones = []
+    for r, st in enumerate(ranks):
+      done = ctypes.c_int32(0)
+      _lib._check(lib.sfem_cg_read(_lib.ptr(st['state']),
+                                   ctypes.byref(infos[r]), ctypes.byref(done),
+                                   streams[r].cuda_stream), 'sfem_cg_read')
+      dones.append(done.value)
+    assert 2 not in dones, 'a peer-memory wait timed out'
+    assert len(set(dones)) == 1, dones   # identical decision on every rank
+    if dones[0]:
+      break
+    for r, st in enumerate(ranks):
+      _lib._check(lib.sfem_cg_iterate(
+          st['op'].handle, plans[r].p2p_handle(st['rhs']), sx[r].handle, 0.0,
+          1.0, blks[r].num_interface_elements, 1, _lib.ptr(st['x']),
+          _lib.ptr(st['r']), _lib.ptr(st['p']), _lib.ptr(st['ap']),
+          _lib.ptr(st['minv']), _lib.ptr(st['owned']), _lib.ptr(st['state']),
+          check_every, streams[r].cuda_stream), 'sfem_cg_iterate')
+  torch.cuda.synchronize()
+  for r in range(world):
+    assert not plans[r].p2p_timed_out(device) and not sx[r].timed_out()
+  # oracle: the unpartitioned solve
+  ref = refine_premesh(unit_cube_mesh(ne, ndim=ndim, a=-1., b=1.), grid1d)
+  bmask = ref.finalize_host()['physical_masks']['boundary']
+  interior = 1.0 - bmask
+  oracle = dense.FESpace(bench_deform(ref.node_coords), ref.elements, n1d,
+                         helpers.TNAME[GLL], n1d, helpers.TNAME[GLL])
+  gb = oracle.apply(np.ones(ref.num_nodes), 1.0, 0.0, interior)
+  gd = oracle.stiffness_diag(interior)
+  gminv = np.where(gd != 0, 1.0 / np.where(gd != 0, gd, 1.0), 0.0)
+  gx, ginfo = dense.cg(lambda v: oracle.apply(v, interior_mask=interior), gb,
+                       tol=tol, M=lambda v: gminv * v)
+  counts = {int(i.num_iterations) for i in infos}
+  assert len(counts) == 1
+  assert abs(counts.pop() - ginfo['num_iterations']) <= 1
+  for r in range(world):
+    l2g = local_to_global(ref.node_coords, blks[r].premesh.node_coords)
+    assert rel_err(ranks[r]['rhs'].cpu(), gb[l2g]) < 1e-12
+    assert rel_err(ranks[r]['x'].cpu(), gx[l2g]) < 1e-7
+
+
 def test_multi_gpu_partitioned_parity():
   """2 ranks over NCCL vs the unpartitioned solve (needs >= 2 GPUs)."""
   import os
