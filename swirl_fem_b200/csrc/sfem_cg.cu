@@ -212,9 +212,23 @@ __device__ __forceinline__ typename Vec<T>::type vpack(const T (&v)[Vec<T>::W]) 
   return t;
 }
 
-__device__ __forceinline__ void spin_until(const unsigned long long* flag,
+// Bounded (~6 s of globaltimer: longer than the 4 s a peer wait may take in
+// the publishing CTA): a grid that could not make progress must not hang the
+// device.  Returns false on a timeout.
+__device__ __forceinline__ bool spin_until(const unsigned long long* flag,
                                            unsigned long long want) {
-  while (ld_acquire_gpu64(flag) < want) __nanosleep(20);
+  uint64_t t0 = 0;
+  unsigned spins = 0;
+  while (ld_acquire_gpu64(flag) < want) {
+    __nanosleep(20);
+    if ((++spins & 4095u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 6000000000ull) return false;
+    }
+  }
+  return true;
 }
 
 template <typename T>
@@ -245,7 +259,8 @@ cg_step_kernel(int64_t n, T* __restrict__ x, T* __restrict__ r,
         st_release_gpu(&st->ready0, seq + 1);
       }
     }
-    if (threadIdx.x == 0) spin_until(&st->ready0, seq + 1);
+    if (threadIdx.x == 0 && !spin_until(&st->ready0, seq + 1))
+      vst->done = 2.0;
     __syncthreads();
   }
   const T alpha = dist ? (T)vst->alpha : (T)(vst->gamma / vst->pAp);
@@ -316,7 +331,7 @@ cg_step_kernel(int64_t n, T* __restrict__ x, T* __restrict__ r,
       st_release_gpu(&st->ready1, seq + 1);
     }
   }
-  if (threadIdx.x == 0) spin_until(&st->ready1, seq + 1);
+  if (threadIdx.x == 0 && !spin_until(&st->ready1, seq + 1)) vst->done = 2.0;
   __syncthreads();
   const T beta = (T)vst->beta;
 

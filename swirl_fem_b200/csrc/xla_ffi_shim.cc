@@ -4,10 +4,15 @@
 //
 // HEADER-GATED: jax / jaxlib (and therefore xla/ffi/api/ffi.h) are NOT
 // installed in the build image and there is no network, so this file compiles
-// to an empty translation unit here and is NOT part of libswirl_b200.so.  It
-// is the binding a maintainer of the reference builds next to jaxlib:
-//   g++ -shared -fPIC -I$(python -c "import jaxlib; print(jaxlib.__path__[0])")/include \
-//       xla_ffi_shim.cc -L../lib -lswirl_b200 -o libswirl_b200_xla.so
+// to an empty translation unit here and is NOT part of libswirl_b200.so.  The
+// CPU suite compiles it against an inert mock of that header
+// (tests/mock_xla/, tests/test_xla_ffi_shim.py): every handler's signature is
+// checked against its Ffi::Bind() operand list and every C entry point it
+// calls against include/swirl_b200.h, and the object is linked against
+// libswirl_b200.so.  It is the binding a maintainer of the reference builds
+// next to jaxlib:
+//   g++ -shared -fPIC -I$(python -c "import jaxlib; print(jaxlib.__path__[0])")/include
+//       xla_ffi_shim.cc -L../lib -lswirl_b200 -o libswirl_b200_xla.so   (one command line)
 // The tested binding of the same C symbols is ctypes + torch (swirl_fem_b200/_lib.py).
 #if __has_include("xla/ffi/api/ffi.h")
 
@@ -137,10 +142,12 @@ static ffi::Error EvalTransposeImpl(cudaStream_t stream, ffi::AnyBuffer vals,
                                     ffi::AnyBuffer grads,
                                     ffi::Result<ffi::AnyBuffer> out,
                                     int64_t space, int64_t ncomp) {
+  // a zero-sized operand stands for "no such coefficient field" (NULL in C)
   return Status(sfem_space_eval_transpose(
-      reinterpret_cast<const sfem_space*>(space), vals.untyped_data(),
-      grads.untyped_data(), (int32_t)ncomp, out->untyped_data(),
-      (sfem_stream_t)stream));
+      reinterpret_cast<const sfem_space*>(space),
+      vals.element_count() ? vals.untyped_data() : nullptr,
+      grads.element_count() ? grads.untyped_data() : nullptr, (int32_t)ncomp,
+      out->untyped_data(), (sfem_stream_t)stream));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(sfem_xla_space_eval_transpose, EvalTransposeImpl,
                               ffi::Ffi::Bind()
@@ -150,5 +157,90 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(sfem_xla_space_eval_transpose, EvalTransposeImpl,
                                   .Ret<ffi::AnyBuffer>()
                                   .Attr<int64_t>("space")
                                   .Attr<int64_t>("ncomp"));
+
+// gather_scatter.exchange, unpartitioned (gather_scatter.py:221-261): in place
+// on a copy of u; `scratch` is an XLA-allocated (num_unique,) work buffer.
+static ffi::Error ExchangeImpl(cudaStream_t stream, ffi::AnyBuffer u,
+                               ffi::Buffer<ffi::DataType::S32> gather_idx,
+                               ffi::Buffer<ffi::DataType::S32> unique_idx,
+                               ffi::Result<ffi::AnyBuffer> out,
+                               ffi::Result<ffi::AnyBuffer> scratch) {
+  const size_t esz = u.element_type() == ffi::DataType::F64 ? 8 : 4;
+  if (cudaMemcpyAsync(out->untyped_data(), u.untyped_data(),
+                      u.element_count() * esz, cudaMemcpyDeviceToDevice,
+                      stream) != cudaSuccess)
+    return ffi::Error(ffi::ErrorCode::kInternal, "cudaMemcpyAsync failed");
+  return Status(sfem_exchange(
+      DtypeOf(u.element_type()), out->untyped_data(), gather_idx.typed_data(),
+      unique_idx.element_count() ? unique_idx.typed_data() : nullptr,
+      (int64_t)gather_idx.element_count(), (int64_t)scratch->element_count(), 1,
+      0, scratch->untyped_data(), (sfem_stream_t)stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(sfem_xla_exchange, ExchangeImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::Buffer<ffi::DataType::S32>>()
+                                  .Arg<ffi::Buffer<ffi::DataType::S32>>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>());
+
+// linalg.cg.cg (swirl_fem/linalg/cg.py:30-97) with A = the fused operator and
+// M = Jacobi or identity: x holds x0 on entry (an aliased input/output pair in
+// jax.ffi.ffi_call(..., input_output_aliases={1: 0})); `workspace` is an
+// XLA-allocated byte buffer of sfem_cg_workspace_bytes(); `info` receives
+// (residual, iterations) as two doubles.
+static ffi::Error CgImpl(cudaStream_t stream, ffi::AnyBuffer b,
+                         ffi::AnyBuffer x0, ffi::AnyBuffer minv,
+                         ffi::Result<ffi::AnyBuffer> x,
+                         ffi::Result<ffi::AnyBuffer> workspace,
+                         ffi::Result<ffi::Buffer<ffi::DataType::F64>> info,
+                         int64_t handle, double tol, double atol,
+                         int64_t maxiter, double lam, double mu) {
+  const auto dims = b.dimensions();
+  const int ncomp = dims.size() == 2 ? (int)dims[1] : 1;
+  const size_t esz = b.element_type() == ffi::DataType::F64 ? 8 : 4;
+  if (x->untyped_data() != x0.untyped_data() &&
+      cudaMemcpyAsync(x->untyped_data(), x0.untyped_data(),
+                      b.element_count() * esz, cudaMemcpyDeviceToDevice,
+                      stream) != cudaSuccess)
+    return ffi::Error(ffi::ErrorCode::kInternal, "cudaMemcpyAsync failed");
+  sfem_cg_params prm;
+  prm.tol = tol;
+  prm.atol = atol;
+  prm.maxiter = maxiter;
+  prm.precond = minv.element_count() ? 1 : 0;
+  prm.check_every = 16;
+  prm.lambda = lam;
+  prm.mu = mu;
+  sfem_cg_info out_info;
+  const int rc = sfem_cg(
+      reinterpret_cast<const sfem_op*>(handle), b.untyped_data(),
+      x->untyped_data(), ncomp,
+      minv.element_count() ? minv.untyped_data() : nullptr, &prm,
+      workspace->untyped_data(), &out_info, (sfem_stream_t)stream);
+  if (rc != SFEM_OK) return Status(rc);
+  const double host[2] = {out_info.residual, (double)out_info.num_iterations};
+  if (cudaMemcpyAsync(info->typed_data(), host, sizeof(host),
+                      cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+      cudaStreamSynchronize(stream) != cudaSuccess)
+    return ffi::Error(ffi::ErrorCode::kInternal, "cudaMemcpyAsync failed");
+  return ffi::Error::Success();
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(sfem_xla_cg, CgImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Ret<ffi::Buffer<ffi::DataType::F64>>()
+                                  .Attr<int64_t>("handle")
+                                  .Attr<double>("tol")
+                                  .Attr<double>("atol")
+                                  .Attr<int64_t>("maxiter")
+                                  .Attr<double>("lam")
+                                  .Attr<double>("mu"));
 
 #endif  // __has_include("xla/ffi/api/ffi.h")
