@@ -57,6 +57,7 @@ def parse_args():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-e2e', action='store_true')
   ap.add_argument('--no-parity', action='store_true')
+  ap.add_argument('--no-extra', action='store_true')
   return ap.parse_args()
 
 
@@ -150,14 +151,22 @@ def measured_peak_gbs():
 
 def cpu_oracle_throughput(ndim, order, budget_s=12.0, ne_sample=None):
   """GDOF/s of the numpy oracle (dense Kronecker algorithm of the reference,
-  batched GEMM) on a bounded sample of the same workload."""
+  batched GEMM) on a bounded sample of the same workload: a mesh of the same
+  shape that is far larger than the host caches (3-D: ne = 16, 1.44 M dofs,
+  0.4 GB of geometric data), all host cores (element chunks on a thread pool,
+  BLAS pinned to one thread per chunk), median over the per-apply times."""
   from oracle import dense
   from swirl_fem_b200.common.premesh_commons import unit_cube_mesh
   from swirl_fem_b200.core.interpolation import Nodes1D, NodeType
   from swirl_fem_b200.core.mesh_refiner import refine_premesh
+  try:
+    from threadpoolctl import threadpool_limits
+  except ImportError:  # BLAS threads then oversubscribe the chunks
+    import contextlib
+    threadpool_limits = lambda limits: contextlib.nullcontext()  # noqa: E731
   n1d = order + 1
   if ne_sample is None:
-    ne_sample = 6 if ndim == 3 else 48
+    ne_sample = 16 if ndim == 3 else 128
   gll = NodeType.GAUSS_LOBATTO_LEGENDRE
   refined = refine_premesh(unit_cube_mesh(ne_sample, ndim=ndim, a=-1., b=1.),
                            Nodes1D.create(n1d, gll))
@@ -165,26 +174,31 @@ def cpu_oracle_throughput(ndim, order, budget_s=12.0, ne_sample=None):
   fes = dense.FESpace(coords, refined.elements, n1d, 'gauss_lobatto_legendre',
                       n1d, 'gauss_lobatto_legendre')
   u = np.random.default_rng(0).standard_normal(refined.num_nodes)
-  fes.apply_gemm(u)  # warm-up (BLAS threads, caches)
-  t0 = time.perf_counter()
-  reps = 0
-  while True:
-    fes.apply_gemm(u)
-    reps += 1
-    el = time.perf_counter() - t0
-    if el > budget_s or reps >= 200:
-      break
   cores = len(os.sched_getaffinity(0))
+  times = []
+  with threadpool_limits(limits=1):
+    fes.apply_gemm(u, threads=cores)  # warm-up
+    t0 = time.perf_counter()
+    while True:
+      t1 = time.perf_counter()
+      fes.apply_gemm(u, threads=cores)
+      times.append(time.perf_counter() - t1)
+      if (time.perf_counter() - t0 > budget_s and len(times) >= 5) or len(
+          times) >= 200:
+        break
+  med = float(np.median(times))
   return {
-      'value': refined.num_nodes * reps / el / 1e9,
+      'value': refined.num_nodes / med / 1e9,
       'unit': 'GDOF/s',
       'cores': cores,
       'kind': 'port',
       'sample': (f'{ndim}-D ne={ne_sample} order {order} '
-                 f'({refined.num_nodes} dofs), {reps} applies in {el:.1f} s, '
-                 'numpy restatement of the reference dense-Kronecker apply '
-                 '(JAX unavailable in image)'),
-      'ms_per_step': el / reps * 1e3,
+                 f'({refined.num_nodes} dofs), median of {len(times)} applies '
+                 f'({sum(times):.1f} s), numpy restatement of the reference '
+                 'dense-Kronecker apply on all host cores (JAX unavailable in '
+                 'image)'),
+      'ms_per_step': med * 1e3,
+      'spread': float((max(times) - min(times)) / med),
   }
 
 
@@ -201,9 +215,10 @@ def run_reference(args):
       'ms_per_step': res['ms_per_step'], 'higher_is_better': True,
       'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
       'data': 'synthetic',
-      'config': {'workload': config_name(args), 'note': (
-          'reference algorithm on host cores over a bounded sample of the '
-          'workload (the dense path is ~55x the flops of sum-factorisation)')},
+      'config': bench_config(args, args.gpus),
+      'note': ('reference algorithm on host cores over a bounded sample of '
+               'the workload (the dense path is ~55x the flops of '
+               'sum-factorisation)'),
       'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind',
                                            'sample')},
       'e2e': {'value': res['value'], 'unit': 'GDOF/s',
@@ -211,6 +226,16 @@ def run_reference(args):
       'gpu_launches': 0,
   }
   print(json.dumps(line), flush=True)
+
+
+def bench_config(args, world):
+  """`config` of the JSON line: identical for both arms at the same N."""
+  from swirl_fem_b200.communication.partition import GRID_FOR_WORLD
+  grid = GRID_FOR_WORLD[args.dim][world]
+  return {'workload': config_name(args),
+          'partition': 'x'.join(str(g) for g in grid),
+          'l2_policy': 'inputs larger than L2 (geometric factors alone are '
+                       'tens of L2 sizes per rank)'}
 
 
 def config_name(args):
@@ -501,28 +526,31 @@ def run_ours(args):
               'kernel_ms': apply_ms,
               'frac_of_nominal_8TBs': achieved / 8000.0}
 
-  # end to end through the public API with pinned host buffers
+  # end to end through the public API with pinned HOST buffers: every step
+  # uploads its x, applies, downloads its y (core.operator.HostPipeline: the
+  # upload of step i+1, the apply of step i and the download of step i-1
+  # overlap; PCIe is full duplex)
   e2e = None
   if not args.no_e2e:
-    xh = torch.empty(mesh.num_nodes, dtype=dtype).pin_memory()
-    yh = torch.empty(mesh.num_nodes, dtype=dtype).pin_memory()
-    xh.copy_(x)
-    xd = torch.empty_like(x)
-    n_e2e = max(2, min(args.steps, 5))
-
-    def e2e_step():
-      xd.copy_(xh, non_blocking=True)
-      op.apply_partitioned(xd, y, halo, blk.num_interface_elements, lam=0.0,
-                           mu=1.0)
-      yh.copy_(y, non_blocking=True)
-
-    e2e_step()
+    from swirl_fem_b200.core.operator import HostPipeline
+    n_e2e = max(4, min(args.steps, 8))
+    xh = [torch.empty(mesh.num_nodes, dtype=dtype).pin_memory()
+          for _ in range(2)]
+    yh = [torch.empty(mesh.num_nodes, dtype=dtype).pin_memory()
+          for _ in range(2)]
+    for t in xh:
+      t.copy_(x)
+    pipe = HostPipeline(op, halo, blk.num_interface_elements, depth=2)
+    for i in range(2):
+      pipe.submit(xh[i % 2], yh[i % 2])
+    pipe.synchronize()
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(
         enable_timing=True)
     a.record()
-    for _ in range(n_e2e):
-      e2e_step()
+    for i in range(n_e2e):
+      pipe.submit(xh[i % 2], yh[i % 2])
+    pipe.drain()
     b.record()
     barrier()
     e2e_ms = a.elapsed_time(b) / n_e2e
@@ -530,10 +558,15 @@ def run_ours(args):
       t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
       e2e_ms = float(t.item())
+    y_check = float((yh[(n_e2e - 1) % 2].to(device) - y).abs().max())
     e2e = {'value': num_global / (e2e_ms * 1e-3) / 1e9, 'unit': 'GDOF/s',
            'h2d_bytes_per_step': int(mesh.num_nodes * esz),
            'd2h_bytes_per_step': int(mesh.num_nodes * esz),
-           'ms_per_step': e2e_ms, 'steps': n_e2e}
+           'ms_per_step': e2e_ms, 'steps': n_e2e,
+           'pipeline': 'HostPipeline depth 2: H2D(i+1) | apply(i) | D2H(i-1) '
+                       'on three streams, pinned host buffers',
+           'max_abs_diff_vs_device_resident_result': y_check}
+    del pipe
 
   # fused CG: fixed iteration count (tol = 0 never converges early)
   cg_info = None
@@ -546,12 +579,9 @@ def run_ours(args):
       halo.exchange_(diag)
     minv_t = torch.where(diag != 0, 1.0 / diag, torch.zeros_like(diag))
 
-    # SFEM_CG_SCALARS=p2p: all-reduce the two dot products per iteration over
-    # peer memory (one single-CTA kernel each) instead of NCCL
+    # the two dot products per iteration are all-reduced over peer memory
+    # inside the fused step kernel (distributed_cg creates the exchange)
     sx = None
-    if world > 1 and os.environ.get('SFEM_CG_SCALARS', 'nccl') == 'p2p':
-      from swirl_fem_b200.communication.scalar_exchange import ScalarExchange
-      sx = ScalarExchange.create(device)
 
     def solve(iters):
       if world == 1:
@@ -576,15 +606,49 @@ def run_ours(args):
       t = torch.tensor([cg_ms], dtype=torch.float64, device=device)
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
       cg_ms = float(t.item())
+    # the same solve end to end: right-hand side from pinned host memory,
+    # the fixed number of iterations, solution back to the host
+    cg_e2e_ms = None
+    if not args.no_e2e:
+      bh = torch.empty(mesh.num_nodes, dtype=dtype).pin_memory()
+      bh.copy_(rhs)
+      xh_out = torch.empty(mesh.num_nodes, dtype=dtype).pin_memory()
+      barrier()
+      a.record()
+      rhs.copy_(bh, non_blocking=True)
+      xs, _ = solve(args.cg_iters)
+      xh_out.copy_(xs, non_blocking=True)
+      b.record()
+      barrier()
+      cg_e2e_ms = a.elapsed_time(b)
+      if world > 1:
+        t = torch.tensor([cg_e2e_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cg_e2e_ms = float(t.item())
     cg_bytes = abytes + 11 * esz * mesh.num_nodes
     cg_info = {'iterations': info['num_iterations'], 'ms_per_iteration': cg_ms,
                'gdof_per_s_iter': num_global / (cg_ms * 1e-3) / 1e9,
                'preconditioner': 'jacobi',
                'roofline_frac': cg_bytes / (cg_ms * 1e-3) / 1e9 / peak,
-               'driver': 'sfem_cg (fused, 1 GPU)' if world == 1 else
-                         ('distributed_cg (fused kernels, scalars over peer '
-                          'memory)' if sx is not None else
-                          'distributed_cg (fused kernels + NCCL scalars)')}
+               'e2e_solve_ms': cg_e2e_ms,
+               'e2e_note': 'b uploaded from pinned host memory, '
+                           f'{args.cg_iters} iterations, x downloaded',
+               'launches_per_iteration': 2 if world == 1 else 3,
+               'driver': 'sfem_cg (apply + one fused step kernel per '
+                         'iteration)' if world == 1 else
+                         'distributed_cg -> sfem_cg_iterate (apply with '
+                         'in-kernel halo push, wait kernel, fused step kernel '
+                         'with the scalar all-reduces over peer memory)'
+                         if halo_path and halo_path.startswith('peer') else
+                         'distributed_cg (building blocks + NCCL scalars)'}
+
+  # configs 1, 2, 3 and a config-5 subset (N = 1 only): bench_extra.py
+  extra = None
+  if rank == 0 and world == 1 and not args.no_extra:
+    import bench_extra
+    del x, y
+    torch.cuda.empty_cache()
+    extra = bench_extra.run_all(device, peak, ClockSampler, local_rank)
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -602,15 +666,13 @@ def run_ours(args):
         'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': args.dtype,
         'data': 'synthetic',
-        'config': {
-            'workload': config_name(args),
-            'partition': 'x'.join(str(g) for g in blk.grid),
+        'config': bench_config(args, world),
+        'details': {
             'halo_exchange': halo_path,
             'halo_timeline': halo_timeline,
             'local_dofs_rank0': mesh.num_nodes,
             'elements_rank0': mesh.num_elements,
-            'l2_policy': 'inputs larger than L2 (geometric factors '
-                         f'{op.geom.numel() * esz / 1e9:.2f} GB per rank)',
+            'geometric_factors_gb_per_rank': op.geom.numel() * esz / 1e9,
             'setup_s': t_setup,
         },
         'clocks': clocks,
@@ -620,6 +682,7 @@ def run_ours(args):
         'cpu_baseline': cpu,
         'cg': cg_info,
         'parity': parity,
+        'extra': extra,
     }
     print(json.dumps(line), flush=True)
   if world > 1:

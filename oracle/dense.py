@@ -226,7 +226,8 @@ class FESpace:
         [self.interp.interpolate(elem_coords[..., k])
          for k in range(self.ndim)], axis=-1)
     # fespace.py:338-340: jacs[m,q,i,j] = d x_j / d xi_i
-    self.jacs = np.einsum('mnj,qni->mqij', elem_coords, self.interp.matrix_grad)
+    self.jacs = np.einsum('mnj,qni->mqij', elem_coords,
+                          self.interp.matrix_grad, optimize=True)
     # fespace.py:345-346 (signed det, no abs)
     self.invjacs = np.linalg.inv(self.jacs)
     self.jacdets = np.linalg.det(self.jacs)
@@ -320,18 +321,39 @@ class FESpace:
     """Lumped mass = scatter(mass_local(1)) (navier_stokes.py:286-287)."""
     return self.scatter(self.mass_local(np.ones(self.elements.shape)))
 
-  def apply_gemm(self, u, mu=1.):
-    """Same stiffness apply routed through batched GEMMs (cpu baseline leg)."""
+  def apply_gemm(self, u, mu=1., threads=1):
+    """Same stiffness apply routed through batched GEMMs (cpu baseline leg).
+    `threads` > 1: the elements are split into chunks that run concurrently
+    (numpy releases the GIL inside matmul / einsum), so the CPU leg uses all
+    the host cores it is given, not only the BLAS-threaded GEMMs."""
     g = self.interp.matrix_grad
     q, n, d = g.shape
-    gm = g.transpose(1, 0, 2).reshape(n, q * d)
+    gm = np.ascontiguousarray(g.transpose(1, 0, 2).reshape(n, q * d))
     ul = self.gather(u)
-    eg = (ul @ gm).reshape(-1, q, d)
-    gu = np.einsum('mqi,mqji->mqj', eg, self.invjacs)
-    wq = gu * (self.jacdets * self.quad_weights)[..., None]
-    ref = np.einsum('mqj,mqji->mqi', wq, self.invjacs)
-    yl = ref.reshape(-1, q * d) @ gm.T
-    return mu * self.scatter(yl)
+    w = self.jacdets * self.quad_weights
+
+    def local(sl):
+      eg = (ul[sl] @ gm).reshape(-1, q, d)
+      gu = np.einsum('mqi,mqji->mqj', eg, self.invjacs[sl])
+      wq = gu * w[sl][..., None]
+      ref = np.einsum('mqj,mqji->mqi', wq, self.invjacs[sl])
+      return ref.reshape(-1, q * d) @ gm.T
+
+    num = ul.shape[0]
+    if threads <= 1 or num < 2 * threads:
+      yl = local(slice(0, num))
+    else:
+      import concurrent.futures  # pylint: disable=g-import-not-at-top
+      bounds = np.linspace(0, num, 4 * threads + 1).astype(int)
+      with concurrent.futures.ThreadPoolExecutor(threads) as pool:
+        parts = list(pool.map(lambda i: local(slice(bounds[i], bounds[i + 1])),
+                              range(4 * threads)))
+      yl = np.concatenate(parts)
+    idx = self.elements.reshape(-1)
+    ok = idx != SENTINEL
+    y = np.bincount(idx[ok], weights=yl.reshape(-1)[ok],
+                    minlength=self.num_nodes)
+    return mu * y
 
 
 # ----------------------------------------------------------------------------

@@ -217,6 +217,64 @@ class FusedOperator:
     return BoundOperator(self, lam, mu)
 
 
+class HostPipeline:
+  """Streams HOST vectors through the operator: `y_host = A(x_host)`.
+
+  PCIe is full duplex, so the upload of vector i+1, the apply of vector i and
+  the download of result i-1 run concurrently: two copy streams next to the
+  compute stream, `depth` device buffers each for x and y, ordered by events
+  only (no host synchronisation per step).  Host tensors must be pinned.
+  """
+
+  def __init__(self, op: 'FusedOperator', halo=None,
+               num_interface_elements: int = 0, depth: int = 2):
+    dev = op.mesh.device
+    self.op, self.halo, self.ni = op, halo, int(num_interface_elements)
+    self.depth, self.count = int(depth), 0
+    self.s_in = torch.cuda.Stream(device=dev)
+    self.s_out = torch.cuda.Stream(device=dev)
+    mk = lambda: torch.empty(op.num_nodes, dtype=op.dtype, device=dev)  # noqa: E731
+    self.xd = [mk() for _ in range(depth)]
+    self.yd = [mk() for _ in range(depth)]
+    ev = lambda: [torch.cuda.Event() for _ in range(depth)]  # noqa: E731
+    self.ev_in, self.ev_apply, self.ev_out = ev(), ev(), ev()
+
+  def submit(self, x_host: torch.Tensor, y_host: torch.Tensor,
+             lam: float = 0.0, mu: float = 1.0):
+    """Enqueues upload -> apply -> download of one vector; returns at once."""
+    if not (x_host.is_pinned() and y_host.is_pinned()):
+      raise ValueError('HostPipeline needs pinned host tensors')
+    k = self.count % self.depth
+    dev = self.op.mesh.device
+    main = torch.cuda.current_stream(dev)
+    if self.count >= self.depth:
+      self.s_in.wait_event(self.ev_apply[k])   # x buffer k is free again
+      main.wait_event(self.ev_out[k])          # y buffer k has been drained
+    with torch.cuda.stream(self.s_in):
+      self.xd[k].copy_(x_host, non_blocking=True)
+      self.ev_in[k].record(self.s_in)
+    main.wait_event(self.ev_in[k])
+    self.op.apply_partitioned(self.xd[k], self.yd[k], self.halo, self.ni,
+                              lam=lam, mu=mu)
+    self.ev_apply[k].record(main)
+    with torch.cuda.stream(self.s_out):
+      self.s_out.wait_event(self.ev_apply[k])
+      y_host.copy_(self.yd[k], non_blocking=True)
+      self.ev_out[k].record(self.s_out)
+    self.count += 1
+
+  def drain(self):
+    """Makes the CURRENT stream wait for every submitted download (so an event
+    recorded on it afterwards closes the timed region); no host sync."""
+    main = torch.cuda.current_stream(self.op.mesh.device)
+    for k in range(min(self.count, self.depth)):
+      main.wait_event(self.ev_out[k])
+
+  def synchronize(self):
+    self.drain()
+    torch.cuda.current_stream(self.op.mesh.device).synchronize()
+
+
 class BoundOperator:
   """`A(u)` with fixed (lam, mu); recognised by `linalg.cg.cg` (fused path)."""
 
