@@ -239,9 +239,9 @@ __device__ __forceinline__ void bulk_copy_g2s_evict_first(void* smem_dst,
       : "memory");
 }
 
-// CONN2 / EVICT are tuning variants (SFEM_EXPERIMENTS builds only):
+// CONN2 / EVICT: pipeline options chosen per (precision, N) by Tune3D below.
 //   CONN2: the connectivity words are fetched TWO element steps ahead (ncu on
-//          the default kernel: 21 % of all stall samples sit on the first use
+//          the one-step kernel: 21 % of all stall samples sat on the first use
 //          of the next element's connectivity, a DRAM load issued only one
 //          barrier earlier);
 //   EVICT: factors staged with the evict-first copy above.
@@ -787,6 +787,25 @@ struct AutoCfg3D {
   static constexpr int MINB = m0 < 1 ? 1 : (m0 > 8 ? 8 : m0);
 };
 
+// Measured on B200 (profiles/r02_variants_9_10_11_orders.txt, r02_bench_ne68_
+// variant_*.json; 16 M and 108 M dofs): both options together are worth +10 %
+// at N = 8 fp64 (81 % -> 89 % of the HBM roofline at 108 M dofs), +8 % at
+// N = 6 fp64, +1.5 % at N = 8 fp32, and cost 1-4 % for the other measured
+// (precision, N) -- those keep the one-step / default-policy pipeline.
+template <typename T, int N>
+struct Tune3D {
+  static constexpr bool conn2 = false, evict = false;
+};
+template <> struct Tune3D<double, 6> {
+  static constexpr bool conn2 = true, evict = true;
+};
+template <> struct Tune3D<double, 8> {
+  static constexpr bool conn2 = true, evict = true;
+};
+template <> struct Tune3D<float, 8> {
+  static constexpr bool conn2 = true, evict = true;
+};
+
 constexpr int clamp_int(int v, int lo, int hi) {
   return v < lo ? lo : (v > hi ? hi : v);
 }
@@ -828,6 +847,10 @@ int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
         return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
                                true, true>(op, lambda, mu, x, y, ncomp, dot_xy,
                                            stream);
+      case 12:  // neither (the round-1 pipeline)
+        return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
+                               false, false>(op, lambda, mu, x, y, ncomp,
+                                             dot_xy, stream);
       default:
         break;
     }
@@ -865,7 +888,9 @@ int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
     }
   }
 #endif
-  return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH>(
+  using Tn = Tune3D<T, N>;
+  return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
+                         Tn::conn2 && !LOCAL, Tn::evict>(
       op, lambda, mu, x, y, ncomp, dot_xy, stream);
 }
 
@@ -875,8 +900,10 @@ int launch3d_v2_halo(const sfem_op& op, double lambda, double mu, const void* x,
                      void* y, double* dot_xy, cudaStream_t stream) {
   constexpr int EPB = default_epb3d<T, N, MASS>();
   using A = AutoCfg3D<T, N, MASS, EPB>;
-  return launch3d_v2_cfg<T, N, MASS, false, EPB, A::MINB, A::KCH, true>(
-      op, lambda, mu, x, y, 1, dot_xy, stream);
+  using Tn = Tune3D<T, N>;
+  return launch3d_v2_cfg<T, N, MASS, false, EPB, A::MINB, A::KCH, true,
+                         Tn::conn2, Tn::evict>(op, lambda, mu, x, y, 1, dot_xy,
+                                               stream);
 }
 
 }  // namespace

@@ -357,6 +357,9 @@ __device__ __forceinline__ bool scalar_allreduce_warp(const ScalarDev& sx,
     }
   }
   ok = __all_sync(0xffffffffu, ok);
+  // every lane reads every rank's slot, but only lane t acquired slot t:
+  // the warp barrier orders the other lanes' loads after that acquire
+  __syncwarp();
   const ScalarSlot* base =
       reinterpret_cast<const ScalarSlot*>(sx.my_region) + parity * sx.world;
   for (int k = 0; k < count; ++k) {
