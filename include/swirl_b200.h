@@ -62,8 +62,11 @@ int64_t sfem_launch_count(void);
  * Replaces gather_scatter.gather (swirl_fem/core/gather_scatter.py:121-127)
  * and Mesh.gather (swirl_fem/core/mesh.py:155-160).  `out` is written with
  * element stride `stride` too, so a (G,d) AoS field is gathered one component
- * per call (the reference vmaps over the last axis, navier_stokes.py:210-212).
- */
+ * per call (the reference vmaps over the last axis, navier_stokes.py:210-212)
+ * or, with offset = -1, all `stride` components in ONE launch.  The same
+ * convention holds for sfem_scatter_add (which then zeroes the whole
+ * (num_nodes, stride) field) and sfem_exchange (whose scratch then holds
+ * num_unique * stride values). */
 int sfem_gather(int dtype, const void* u, const int32_t* indices,
                 int64_t count, double fill_value, int32_t stride,
                 int32_t offset, void* out, sfem_stream_t stream);

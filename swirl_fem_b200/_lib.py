@@ -261,26 +261,37 @@ def _as_index(indices: torch.Tensor) -> torch.Tensor:
 
 
 def gather(u: torch.Tensor, indices: torch.Tensor, fill_value=SENTINEL):
+  """`u[indices]` (SENTINEL -> fill).  `u` of shape `(G, c)` (AoS, component
+  last) is gathered to `indices.shape + (c,)` in ONE launch."""
   require_cuda(u, indices)
   u = u.contiguous()
   idx = _as_index(indices)
-  out = torch.empty(idx.shape, dtype=u.dtype, device=u.device)
+  ncomp = 1 if u.dim() == 1 else u.shape[-1]
+  shape = tuple(idx.shape) + (() if u.dim() == 1 else (ncomp,))
+  out = torch.empty(shape, dtype=u.dtype, device=u.device)
   with torch.cuda.device(u.device):
     _check(lib().sfem_gather(dtype_code(u.dtype), ptr(u), ptr(idx),
-                             idx.numel(), float(fill_value), 1, 0, ptr(out),
+                             idx.numel(), float(fill_value), ncomp,
+                             0 if u.dim() == 1 else -1, ptr(out),
                              stream_ptr(u.device)), 'sfem_gather')
   return out
 
 
 def scatter(u_local: torch.Tensor, indices: torch.Tensor, num_nodes: int):
+  """Zero-init scatter-add; `u_local` of shape `indices.shape + (c,)` gives
+  `(num_nodes, c)` in ONE launch."""
   require_cuda(u_local, indices)
   u_local = u_local.contiguous()
   idx = _as_index(indices)
-  out = torch.empty(num_nodes, dtype=u_local.dtype, device=u_local.device)
+  vector = u_local.dim() == idx.dim() + 1
+  ncomp = u_local.shape[-1] if vector else 1
+  out = torch.empty((num_nodes, ncomp) if vector else (num_nodes,),
+                    dtype=u_local.dtype, device=u_local.device)
   with torch.cuda.device(u_local.device):
     _check(lib().sfem_scatter_add(dtype_code(u_local.dtype), ptr(u_local),
-                                  ptr(idx), idx.numel(), num_nodes, 1, 0,
-                                  ptr(out), stream_ptr(u_local.device)),
+                                  ptr(idx), idx.numel(), num_nodes, ncomp,
+                                  -1 if vector else 0, ptr(out),
+                                  stream_ptr(u_local.device)),
            'sfem_scatter_add')
   return out
 
@@ -320,8 +331,12 @@ class ScatterPlan:
       self._handle = None
 
 
+_NUM_UNIQUE = {}  # (data_ptr, numel) of a unique-index tensor -> max + 1
+
+
 def exchange(u: torch.Tensor, gather_indices: torch.Tensor,
              unique_indices: torch.Tensor | None):
+  """QQ^T over the (periodic) shared dofs; `(G, c)` fields in ONE call."""
   require_cuda(u, gather_indices, unique_indices)
   out = u.contiguous().clone()
   gi = _as_index(gather_indices)
@@ -329,11 +344,22 @@ def exchange(u: torch.Tensor, gather_indices: torch.Tensor,
   count = gi.numel()
   if count == 0:
     return out
-  num_unique = count if ui is None else int(ui.max().item()) + 1
-  scratch = torch.empty(num_unique, dtype=u.dtype, device=u.device)
+  if ui is None:
+    num_unique = count
+  else:
+    # the only host read of the path: done once per index tensor, so that the
+    # call never synchronises afterwards (CUDA-graph capturable)
+    key = (ui.data_ptr(), ui.numel())
+    num_unique = _NUM_UNIQUE.get(key)
+    if num_unique is None:
+      num_unique = int(ui.max().item()) + 1
+      _NUM_UNIQUE[key] = num_unique
+  ncomp = 1 if u.dim() == 1 else u.shape[-1]
+  scratch = torch.empty(num_unique * ncomp, dtype=u.dtype, device=u.device)
   with torch.cuda.device(u.device):
     _check(lib().sfem_exchange(dtype_code(u.dtype), ptr(out), ptr(gi), ptr(ui),
-                               count, num_unique, 1, 0, ptr(scratch),
+                               count, num_unique, ncomp,
+                               0 if u.dim() == 1 else -1, ptr(scratch),
                                stream_ptr(u.device)), 'sfem_exchange')
   return out
 

@@ -1,6 +1,7 @@
 // C-ABI glue: handles, argument checking and dispatch to the kernel families.
 // See include/swirl_b200.h for the contract of every entry point.
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -120,6 +121,16 @@ static int apply_dispatch(const sfem_op& op, double lambda, double mu,
                                  stream);
 }
 
+// SFEM_PDL=0 (developer switch): plain memsets + ordinary launch instead of the
+// zero-fill kernel + programmatic dependent launch of the 3-D apply.
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SFEM_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 // shared by sfem_op_apply and the CG driver
 // `prezeroed`: y[0 .. n_zero) and *dot_xy are already zero (fused CG loop: the
 // previous cg_step_kernel did it), so no fill is enqueued.
@@ -133,8 +144,8 @@ int op_apply_internal(const sfem_op* op, double lambda, double mu,
   const size_t esz = d.dtype == SFEM_F64 ? 8 : 4;
   // 3-D collocated kernels: zero fill by our own kernel, apply launched as its
   // programmatic dependent (prologue overlaps the fill)
-  const bool pdl = op->variant == 0 && d.collocated && d.dim == 3 &&
-                   d.n1d <= 16 && (op->n_zero > 0 || dot_xy);
+  const bool pdl = pdl_enabled() && op->variant == 0 && d.collocated &&
+                   d.dim == 3 && d.n1d <= 16 && (op->n_zero > 0 || dot_xy);
   sfem_op sub = *op;
   if (prezeroed) {
     sub.pdl = false;

@@ -32,8 +32,14 @@ gather_kernel(const T* __restrict__ u, const int32_t* __restrict__ idx,
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t g = __ldcs(idx + i);
-    out[i * stride + offset] =
-        g == SFEM_SENTINEL ? fill : __ldg(u + (int64_t)g * stride + offset);
+    if (offset >= 0) {
+      out[i * stride + offset] =
+          g == SFEM_SENTINEL ? fill : __ldg(u + (int64_t)g * stride + offset);
+    } else {  // every component of the AoS field in ONE launch
+      for (int c = 0; c < stride; ++c)
+        out[i * stride + c] =
+            g == SFEM_SENTINEL ? fill : __ldg(u + (int64_t)g * stride + c);
+    }
   }
 }
 
@@ -45,9 +51,16 @@ scatter_add_kernel(const T* __restrict__ u_local,
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t g = __ldcs(idx + i);
-    if (g != SFEM_SENTINEL)
-      red_add(out + (int64_t)g * stride + offset,
-              __ldcs(u_local + i * stride + offset));
+    if (g != SFEM_SENTINEL) {
+      if (offset >= 0) {
+        red_add(out + (int64_t)g * stride + offset,
+                __ldcs(u_local + i * stride + offset));
+      } else {
+        for (int c = 0; c < stride; ++c)
+          red_add(out + (int64_t)g * stride + c,
+                  __ldcs(u_local + i * stride + c));
+      }
+    }
   }
 }
 
@@ -125,9 +138,15 @@ exchange_sum_kernel(const T* __restrict__ u, const int32_t* __restrict__ gi,
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t g = gi[i];
-    if (g != SFEM_SENTINEL)
-      red_add(scratch + (ui ? ui[i] : (int32_t)i),
-              u[(int64_t)g * stride + offset]);
+    if (g != SFEM_SENTINEL) {
+      const int64_t slot = ui ? ui[i] : (int32_t)i;
+      if (offset >= 0) {
+        red_add(scratch + slot, u[(int64_t)g * stride + offset]);
+      } else {  // scratch is (num_unique, stride)
+        for (int c = 0; c < stride; ++c)
+          red_add(scratch + slot * stride + c, u[(int64_t)g * stride + c]);
+      }
+    }
   }
 }
 
@@ -140,10 +159,16 @@ exchange_write_kernel(T* __restrict__ u, const int32_t* __restrict__ gi,
        i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t g = gi[i];
     if (g != SFEM_SENTINEL) {
-      T* p = u + (int64_t)g * stride + offset;
-      const T initial = *p;
-      // same expression as gather_scatter.py:261: u + (updates - initial)
-      *p = initial + (scratch[ui ? ui[i] : (int32_t)i] - initial);
+      const int64_t slot = ui ? ui[i] : (int32_t)i;
+      const int c0 = offset >= 0 ? offset : 0;
+      const int c1 = offset >= 0 ? offset + 1 : stride;
+      for (int c = c0; c < c1; ++c) {
+        T* p = u + (int64_t)g * stride + c;
+        const T initial = *p;
+        // same expression as gather_scatter.py:261: u + (updates - initial)
+        *p = initial +
+             (scratch[offset >= 0 ? slot : slot * stride + c] - initial);
+      }
     }
   }
 }
@@ -331,10 +356,10 @@ template <typename T>
 static int scatter_impl(const void* ul, const int32_t* idx, int64_t count,
                         int64_t num_nodes, int stride, int offset, void* out,
                         cudaStream_t stream) {
-  if (stride == 1) {
-    SFEM_CUDA_CHECK(
-        cudaMemsetAsync(out, 0, sizeof(T) * (size_t)num_nodes, stream));
-  }  // strided (AoS) callers zero the whole field once themselves
+  if (stride == 1 || offset < 0) {
+    SFEM_CUDA_CHECK(cudaMemsetAsync(
+        out, 0, sizeof(T) * (size_t)num_nodes * (size_t)stride, stream));
+  }  // one-component-per-call AoS callers zero the whole field once themselves
   if (count == 0) return SFEM_OK;
   scatter_add_kernel<T><<<blocks_for(count, 4), kThreads, 0, stream>>>(
       (const T*)ul, idx, count, stride, offset, (T*)out);
@@ -402,7 +427,7 @@ int sfem_pointwise(int dtype, int32_t kind, int32_t dim, const void* a,
 int sfem_gather(int dtype, const void* u, const int32_t* indices, int64_t count,
                 double fill_value, int32_t stride, int32_t offset, void* out,
                 sfem_stream_t stream) {
-  SFEM_REQUIRE(count >= 0 && stride >= 1 && offset >= 0 && offset < stride,
+  SFEM_REQUIRE(count >= 0 && stride >= 1 && offset >= -1 && offset < stride,
                "sfem_gather: bad count/stride/offset");
   return dtype == SFEM_F64
              ? sfem::gather_impl<double>(u, indices, count, fill_value, stride,
@@ -414,7 +439,7 @@ int sfem_gather(int dtype, const void* u, const int32_t* indices, int64_t count,
 int sfem_scatter_add(int dtype, const void* u_local, const int32_t* indices,
                      int64_t count, int64_t num_nodes, int32_t stride,
                      int32_t offset, void* out, sfem_stream_t stream) {
-  SFEM_REQUIRE(count >= 0 && stride >= 1 && offset >= 0 && offset < stride,
+  SFEM_REQUIRE(count >= 0 && stride >= 1 && offset >= -1 && offset < stride,
                "sfem_scatter_add: bad count/stride/offset");
   return dtype == SFEM_F64
              ? sfem::scatter_impl<double>(u_local, indices, count, num_nodes,
@@ -524,8 +549,12 @@ int sfem_exchange(int dtype, void* u, const int32_t* gather_indices,
   using namespace sfem;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (count == 0) return SFEM_OK;
+  SFEM_REQUIRE(stride >= 1 && offset >= -1 && offset < stride,
+               "sfem_exchange: bad stride/offset");
   const size_t esz = dtype == SFEM_F64 ? 8 : 4;
-  SFEM_CUDA_CHECK(cudaMemsetAsync(scratch, 0, esz * (size_t)num_unique, stream));
+  SFEM_CUDA_CHECK(cudaMemsetAsync(
+      scratch, 0, esz * (size_t)num_unique * (size_t)(offset < 0 ? stride : 1),
+      stream));
   const int blocks = blocks_for(count);
   if (dtype == SFEM_F64) {
     exchange_sum_kernel<double><<<blocks, kThreads, 0, stream>>>(

@@ -54,6 +54,7 @@ int launch_apply3d_halo(const sfem_op& op, double lambda, double mu,
 int op_apply_internal(const sfem_op* op, double lambda, double mu,
                       const void* x, void* y, int ncomp, double* dot_xy,
                       cudaStream_t stream, bool prezeroed = false);
+bool pdl_enabled();
 
 namespace {
 
@@ -196,7 +197,13 @@ int op_apply_halo_internal(const sfem_op* op, sfem_halo* halo, double lambda,
   }
   const size_t esz = d.dtype == SFEM_F64 ? 8 : 4;
   bool pdl = !prezeroed && (op->n_zero > 0 || dot_xy);
-  if (pdl) {
+  if (pdl && !pdl_enabled()) {
+    pdl = false;
+    if (op->n_zero > 0)
+      SFEM_CUDA_CHECK(cudaMemsetAsync(y, 0, esz * (size_t)op->n_zero, stream));
+    if (dot_xy)
+      SFEM_CUDA_CHECK(cudaMemsetAsync(dot_xy, 0, sizeof(double), stream));
+  } else if (pdl) {
     int rc = launch_zero_fill(y, esz * (size_t)op->n_zero, dot_xy, stream,
                               &pdl);
     if (rc) return rc;

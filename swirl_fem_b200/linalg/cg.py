@@ -10,9 +10,15 @@ Two execution paths, both CUDA:
     `JacobiPreconditioner` -> one call of the C-ABI `sfem_cg`: operator apply
     with p.Ap in its epilogue, one update kernel, one direction kernel, all
     scalars and the convergence flag on the device.
-  * generic: `A`, `M`, `dot_fn` are arbitrary callables on pytrees of CUDA
-    tensors (e.g. `M = velocity.exchange`, navier_stokes.py:437) -> host loop
-    over the same recurrence using the fused `axpby` / `dot` kernels.
+  * device-state: `A` and `M` are arbitrary callables on ONE CUDA tensor
+    (e.g. `H_` with `M = velocity.exchange`, `E = D Q D^T` with the null-space
+    projector, navier_stokes.py:436-452) and `dot_fn` is the default -> the
+    same recurrence on the device-resident state of `sfem_cg_*`: the dot
+    products land in the state, `alpha` / `beta` are formed inside the vector
+    kernels, and the host only reads the convergence flag every `check_every`
+    iterations (no `float()` per dot product, no clones).
+  * generic: pytrees or a user `dot_fn` -> host loop over the same recurrence
+    using the fused `axpby` / `dot` kernels.
 """
 
 from __future__ import annotations
@@ -85,13 +91,127 @@ def _fused_cg(A: BoundOperator, b, x0, tol, atol, maxiter, M, check_every):
   return x, {'residual': residual, 'num_iterations': int(info.num_iterations)}
 
 
+def _device_state_cg(A, b, x0, tol, atol, maxiter, M, check_every,
+                     graph=None):
+  """cg.py:54-97 for callables `A`, `M` on one CUDA tensor, scalars on the
+  device.  Per iteration: A, dot(p, Ap) -> state, `sfem_cg_update` (x, r with
+  alpha = gamma / p.Ap formed in the kernel), M, dot(r, z) -> state,
+  `sfem_cg_direction` (p = z + beta p), `sfem_cg_advance`; once the flag is
+  set the vector kernels are no-ops, so the count equals the reference's.
+
+  `graph` (default: env SFEM_CG_GRAPH, on): the iteration body -- whatever
+  kernels `A` and `M` launch plus the five above -- is captured ONCE into a
+  CUDA graph after a first eager iteration and replayed; the body is static
+  because every scalar lives in the device state.  For the launch-bound
+  Stokes solves (dozens of small kernels per iteration) this removes the
+  per-launch host cost.  Callables that cannot be captured (host
+  synchronisation inside) fall back to eager launches."""
+  import os  # pylint: disable=g-import-not-at-top
+  if graph is None:
+    graph = os.environ.get('SFEM_CG_GRAPH', '1') != '0'
+  lib = _lib.lib()
+  dev, dtype = b.device, b.dtype
+  code = _lib.dtype_code(dtype)
+  b = b.contiguous()
+  n = b.numel()
+  if maxiter is None:
+    maxiter = 10 * n
+  x = torch.zeros_like(b) if x0 is None else x0.to(dtype).clone().contiguous()
+  state = torch.zeros(int(lib.sfem_cg_state_bytes()) // 8, dtype=torch.float64,
+                      device=dev)
+  stream = _lib.stream_ptr(dev)
+  identity = M is None
+
+  def as_vec(t):
+    t = t.to(dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+  with torch.cuda.device(dev):
+    r = b.clone()
+    _lib.axpby(-1.0, as_vec(A(x)), 1.0, r)                  # r = b - A x0
+    z = r if identity else as_vec(M(r))
+    p = z.clone()
+    # n = 0: only (re)initialises the state (tol, atol, maxiter)
+    _lib._check(lib.sfem_cg_init(code, 0, _lib.ptr(b), _lib.ptr(r), None, None,
+                                 _lib.ptr(r), _lib.ptr(p), _lib.ptr(state),
+                                 float(tol), float(atol), int(maxiter), stream),
+                'sfem_cg_init')
+    _lib._check(lib.sfem_dot(code, n, _lib.ptr(r), _lib.ptr(z),
+                             _lib.ptr(state[2:3]), stream), 'sfem_dot')
+    _lib._check(lib.sfem_dot(code, n, _lib.ptr(b), _lib.ptr(b),
+                             _lib.ptr(state[3:4]), stream), 'sfem_dot')
+    _lib._check(lib.sfem_cg_init_finish(_lib.ptr(state), stream),
+                'sfem_cg_init_finish')
+    info = _lib.CgInfo()
+    done = ctypes.c_int32(0)
+    pap, gnew = state[0:1], state[1:2]
+
+    def iteration():
+      """Enqueues one iteration on the CURRENT stream (fixed addresses only:
+      x, r, p and the state are updated in place)."""
+      st = _lib.stream_ptr(dev)
+      ap = as_vec(A(p))
+      _lib._check(lib.sfem_dot(code, n, _lib.ptr(p), _lib.ptr(ap),
+                               _lib.ptr(pap), st), 'sfem_dot')
+      # x += alpha p, r -= alpha Ap (its own r.r lands in gamma_new and is
+      # overwritten by r.z below unless M is the identity)
+      _lib._check(lib.sfem_cg_update(code, n, _lib.ptr(x), _lib.ptr(r),
+                                     _lib.ptr(p), _lib.ptr(ap), None, None,
+                                     _lib.ptr(state), st), 'sfem_cg_update')
+      if identity:
+        zz = r
+      else:
+        zz = as_vec(M(r))
+        _lib._check(lib.sfem_dot(code, n, _lib.ptr(r), _lib.ptr(zz),
+                                 _lib.ptr(gnew), st), 'sfem_dot')
+      _lib._check(lib.sfem_cg_direction(code, n, _lib.ptr(zz), _lib.ptr(p),
+                                        None, _lib.ptr(state), st),
+                  'sfem_cg_direction')
+      _lib._check(lib.sfem_cg_advance(_lib.ptr(state), st), 'sfem_cg_advance')
+
+    captured = None
+    eager_done = 0
+    while True:
+      _lib._check(lib.sfem_cg_read(_lib.ptr(state), ctypes.byref(info),
+                                   ctypes.byref(done), stream), 'sfem_cg_read')
+      if done.value:
+        break
+      iters = int(min(check_every, max(1, maxiter - info.num_iterations)))
+      if graph and captured is None and eager_done == 0:
+        iters = 1   # one eager iteration, then capture
+      if graph and captured is None and eager_done >= 1:
+        # everything lazy (module loading, occupancy queries, cached index
+        # maxima) happened in the eager iteration(s): capture the body now
+        try:
+          g = torch.cuda.CUDAGraph()
+          with torch.cuda.graph(g):
+            iteration()
+          captured = g
+        except Exception:  # pylint: disable=broad-except
+          captured = False   # not capturable: stay eager
+          torch.cuda.synchronize(dev)
+      for _ in range(iters):
+        if captured:
+          captured.replay()
+        else:
+          iteration()
+          eager_done += 1
+  residual = torch.tensor(info.residual, dtype=dtype, device=dev)
+  return x, {'residual': residual, 'num_iterations': int(info.num_iterations)}
+
+
 def cg(A, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None, M=None,
-       dot_fn=None, check_every=16):
+       dot_fn=None, check_every=16, graph=None):
   """Conjugate gradient solver; see the module docstring."""
   if (isinstance(A, BoundOperator) and isinstance(b, torch.Tensor)
       and (M is None or isinstance(M, JacobiPreconditioner))
       and dot_fn is None):
     return _fused_cg(A, b, x0, tol, atol, maxiter, M, check_every)
+  if (isinstance(b, torch.Tensor) and dot_fn is None and b.is_cuda
+      and b.dtype in (torch.float32, torch.float64) and b.numel() > 0
+      and (x0 is None or isinstance(x0, torch.Tensor))):
+    return _device_state_cg(A, b, x0, tol, atol, maxiter, M, check_every,
+                            graph=graph)
 
   if dot_fn is None:
     dot_fn = _default_dot

@@ -219,15 +219,31 @@ class StokesVelocity:
     """Assembled, masked convection term `(u . grad) u` (over-integrated)."""
     return self.interior_mask * self.scatter(self.C_local(self.gather(u)))
 
+  # The reference vmaps the scalar gather / scatter / exchange over the
+  # component axis (navier_stokes.py:210-218); here all components of the AoS
+  # field go through ONE kernel launch (`offset = -1` mode of the C ABI).
   def gather(self, u):
-    return _vmap_last(self.vspace.mesh.gather, u)
+    mesh = self.vspace.mesh
+    if tuple(u.shape[:1]) != (mesh.num_nodes,):
+      raise ValueError(f'Expected `u` to have shape ({mesh.num_nodes}, d) but '
+                       f'got: {tuple(u.shape)}.')
+    return _lib.gather(u, mesh.elements, fill_value=0.)
 
   def scatter(self, u):
-    return _vmap_last(self.vspace.mesh.scatter, u)
+    mesh = self.vspace.mesh
+    return _lib.scatter(u, mesh.elements, mesh.num_nodes)
 
   def exchange(self, u):
-    """QQ^T per component (periodic / shared dofs get the sum of their copies)."""
-    return _vmap_last(self.vspace.mesh.exchange, u)
+    """QQ^T of every component (periodic / shared dofs get the sum of their
+    copies)."""
+    mesh = self.vspace.mesh
+    if mesh.axis_name is not None:
+      return _vmap_last(mesh.exchange, u)
+    if (mesh.exchange_gather_indices is None or
+        mesh.exchange_gather_indices.numel() == 0):
+      return u
+    return _lib.exchange(u, mesh.exchange_gather_indices,
+                         mesh.exchange_unique_indices)
 
   def _vector_covector(self, form, u_local):
     trial = self.vspace.vector_function(u_local)

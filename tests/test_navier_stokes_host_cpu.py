@@ -261,6 +261,14 @@ def test_create_wiring_with_stub_spaces(monkeypatch):
                       lambda premesh, gridpoints_1d: StubRefined(
                           premesh, gridpoints_1d))
   monkeypatch.setattr(ns, 'FiniteElementSpace', StubSpace)
+  # the AoS scatter is ONE C-ABI launch for all components (`_lib.scatter`)
+
+  def stub_vector_scatter(u_local, indices, num_nodes):
+    assert tuple(u_local.shape[:2]) == tuple(indices.shape)
+    return torch.full((num_nodes,) + tuple(u_local.shape[2:]), 2.0,
+                      dtype=torch.float64)
+
+  monkeypatch.setattr(ns._lib, 'scatter', stub_vector_scatter)  # pylint: disable=protected-access
   order = 5
   sem = ns.StokesSEM.create(
       helpers.stokes_vortices_premesh(2),
