@@ -21,6 +21,7 @@
 #include "sfem_common.cuh"
 #include "sfem_apply3d_v2.cuh"
 #include "sfem_apply2d_v2.cuh"
+#include "sfem_apply2d_warp.cuh"
 
 namespace sfem {
 
@@ -310,11 +311,15 @@ DMat<T, N> make_dmat(const SpaceBase& b) {
 template <typename T, int N, bool MASS, bool LOCAL>
 int launch2d(const sfem_op& op, double lambda, double mu, const void* x,
              void* y, int ncomp, double* dot_xy, cudaStream_t stream) {
-  // variant 2 selects the thread-per-node kernel (v1); default is the
-  // two-mapping kernel (v2)
-  if (op.variant != 2)
+  // default: the warp-autonomous kernel (v3); variant 3 selects the
+  // block-synchronous two-mapping kernel (v2), variant 2 the thread-per-node
+  // kernel (v1)
+  if (op.variant == 3)
     return launch2d_v2<T, N, MASS, LOCAL>(op, lambda, mu, x, y, ncomp, dot_xy,
                                           stream);
+  if (op.variant != 2)
+    return launch2d_warp<T, N, MASS, LOCAL>(op, lambda, mu, x, y, ncomp,
+                                            dot_xy, stream);
   using C = Cfg2D<N>;
   const int64_t E = op.base.desc.num_elements;
   const int64_t nblocks = (E + C::epb - 1) / C::epb;

@@ -361,9 +361,12 @@ def test_operator_apply_matches_oracle(case, dtype):
     oracle32 = dense.FESpace(refined.node_coords, refined.elements, n1d,
                              helpers.TNAME[GLL], q1d, helpers.TNAME[qt],
                              dtype=np.float32)
-  # 0: default specialised kernels (three-/two-mapping, bulk-async staging),
-  # 1: generic runtime-(N, Q) kernel, 2: v1 specialised kernels
+  # 0: default specialised kernels (3-D three-mapping with bulk-async staging,
+  # 2-D warp-autonomous), 1: generic runtime-(N, Q) kernel, 2: v1 specialised
+  # kernels, 3 (2-D): the block-synchronous two-mapping kernel
   variants = [0, 1, 2] if qt == GLL and q1d == n1d and ndim > 1 else [0]
+  if len(variants) > 1 and ndim == 2:
+    variants.append(3)
   for lam, mu in ((0.0, 1.0), (1.0, 0.0), (1833.3, 0.7)):
     want = oracle.apply(u, lam=lam, mu=mu, interior_mask=interior)
     if oracle32 is not None:
