@@ -288,9 +288,14 @@ class HaloPlan:
         if region.value:
           lib.sfem_ipc_free(region.value)
       return False
+    self.group = group   # disable_p2p's barrier runs on the same group
     if self.peers:
       self._p2p_attach(dtype, device, region.value, bases, all_splits)
       self._p2p['mapped'] = bases
+    else:
+      # no peers: nothing to exchange, but the region is ours to release
+      self._p2p = {'handle': None, 'dtype': None, 'device': device,
+                   'region': region.value, 'mapped': {}, 'keep': ()}
     torch.cuda.synchronize(device)
     dist.barrier(group=group)
     return True
@@ -326,7 +331,8 @@ class HaloPlan:
     lib = _lib.lib()
     with torch.cuda.device(p['device']):
       torch.cuda.synchronize(p['device'])
-      lib.sfem_halo_destroy(p['handle'])
+      if p['handle'] is not None:
+        lib.sfem_halo_destroy(p['handle'])
       for addr in p.get('mapped', {}).values():
         lib.sfem_ipc_close(addr)
       if 'mapped' in p:
@@ -334,6 +340,9 @@ class HaloPlan:
         dist.barrier(group=self.group)
       lib.sfem_ipc_free(p['region'])
     self._p2p = None
+    sx = self._dev.pop(('sx', str(p['device'])), None)
+    if sx is not None:
+      sx.close(group=self.group)
 
   def scalar_exchange(self, device, group=None):
     """The `ScalarExchange` of this partition (collective on first use; None
@@ -346,14 +355,15 @@ class HaloPlan:
 
   def p2p_handle(self, u: torch.Tensor):
     p = getattr(self, '_p2p', None)
-    if p is None or p['dtype'] != u.dtype or u.dim() != 1:
+    if (p is None or p['handle'] is None or p['dtype'] != u.dtype
+        or u.dim() != 1):
       return None
     return p['handle']
 
   def p2p_set_option(self, key: int, value: int):
     """0: slice size, 1: fuse the canonical sum into the apply kernel."""
     p = getattr(self, '_p2p', None)
-    if p is not None:
+    if p is not None and p['handle'] is not None:
       _lib._check(_lib.lib().sfem_halo_set_option(p['handle'], key, value),
                   'sfem_halo_set_option')
 
@@ -371,7 +381,7 @@ class HaloPlan:
 
   def p2p_timed_out(self, device) -> bool:
     p = getattr(self, '_p2p', None)
-    if p is None:
+    if p is None or p['handle'] is None:
       return False
     with torch.cuda.device(device):
       return bool(_lib.lib().sfem_halo_timed_out(p['handle'],

@@ -25,6 +25,7 @@ class ScalarExchange:
   def __init__(self, rank, world, device, region, peer_regions, mapped=()):
     self.rank, self.world, self.device = rank, world, device
     self.region, self.mapped = region, list(mapped)
+    self.owns_region = True
     addrs = np.asarray(peer_regions, dtype=np.uint64)
     handle = ctypes.c_void_p()
     with torch.cuda.device(device):
@@ -103,6 +104,27 @@ class ScalarExchange:
           self.handle, _lib.ptr(values), values.numel(),
           _lib.stream_ptr(values.device)), 'sfem_scalar_allreduce')
     return values
+
+  def close(self, group=None):
+    """Releases the handle, the mapped peer regions and this rank's region.
+    Collective when the regions were exchanged over IPC (`create`): peers must
+    have stopped publishing before a region is freed."""
+    h = getattr(self, 'handle', None)
+    if not h:
+      return
+    lib = _lib.lib()
+    with torch.cuda.device(self.device):
+      torch.cuda.synchronize(self.device)
+      lib.sfem_scalar_exchange_destroy(h)
+      self.handle = None
+      for addr in self.mapped:
+        lib.sfem_ipc_close(addr)
+      if self.mapped:
+        import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+        dist.barrier(group=group)
+      if self.owns_region and self.region:
+        lib.sfem_ipc_free(self.region)
+    self.mapped, self.region = [], None
 
   def timed_out(self) -> bool:
     with torch.cuda.device(self.device):

@@ -144,8 +144,13 @@ int op_apply_internal(const sfem_op* op, double lambda, double mu,
   const size_t esz = d.dtype == SFEM_F64 ? 8 : 4;
   // 3-D collocated kernels: zero fill by our own kernel, apply launched as its
   // programmatic dependent (prologue overlaps the fill)
+  // Measured (profiles/r02_pdl_on_off.txt): with a SHORT fill (40 MB at 13.6 M
+  // dofs) the overlap is worth 1 %; with a LONG one (320 MB at 108 M dofs) the
+  // apply's CTAs, all parked at griddepcontrol.wait after their first element,
+  // cost 6.7 % -- so the dependent launch is used for fills up to 64 MB only.
   const bool pdl = pdl_enabled() && op->variant == 0 && d.collocated &&
-                   d.dim == 3 && d.n1d <= 16 && (op->n_zero > 0 || dot_xy);
+                   d.dim == 3 && d.n1d <= 16 && (op->n_zero > 0 || dot_xy) &&
+                   esz * (size_t)op->n_zero * ncomp <= ((size_t)64 << 20);
   sfem_op sub = *op;
   if (prezeroed) {
     sub.pdl = false;

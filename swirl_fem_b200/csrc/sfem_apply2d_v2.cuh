@@ -277,7 +277,8 @@ int launch2d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
       ((size_t)C::stage_off + (size_t)EPB * ngeom * C::n) * sizeof(T) +
       (size_t)3 * EPB * C::n * sizeof(uint32_t);
   auto kernel = apply2d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB>;
-  static int per_sm = 0;
+  static int per_sm_dev[64] = {};
+  int& per_sm = per_device_slot(per_sm_dev);
   if (per_sm == 0) {
     if (smem > 48 * 1024)
       SFEM_CUDA_CHECK(cudaFuncSetAttribute(

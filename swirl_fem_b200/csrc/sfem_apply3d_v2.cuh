@@ -711,7 +711,8 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
       sizeof(T);
   auto kernel =
       apply3d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB, KCH, HALO, CONN2, EVICT>;
-  static int per_sm = 0;
+  static int per_sm_dev[64] = {};
+  int& per_sm = per_device_slot(per_sm_dev);
   if (per_sm == 0) {
     if (smem > 48 * 1024)
       SFEM_CUDA_CHECK(cudaFuncSetAttribute(

@@ -311,10 +311,14 @@ DMat<T, N> make_dmat(const SpaceBase& b) {
 template <typename T, int N, bool MASS, bool LOCAL>
 int launch2d(const sfem_op& op, double lambda, double mu, const void* x,
              void* y, int ncomp, double* dot_xy, cudaStream_t stream) {
-  // default: the warp-autonomous kernel (v3); variant 3 selects the
-  // block-synchronous two-mapping kernel (v2), variant 2 the thread-per-node
-  // kernel (v1)
-  if (op.variant == 3)
+  // Two fused kernels with the same arithmetic: the block-synchronous
+  // two-mapping kernel (v2) and the warp-autonomous one (v3).  Measured on B200
+  // at 16 M dofs (profiles/r02_2d_warp_vs_block.txt): v2 wins by 2-20 % up to
+  // N = 10 (both precisions), v3 from N = 12 on (+3 % at N = 12, +42 % fp64 /
+  // +26 % fp32 at N = 16, where v2 fits one or two CTAs per SM).  Variant 3 /
+  // 4 force v2 / v3; variant 2 is the thread-per-node kernel (v1).
+  constexpr bool warp_default = N >= 12;
+  if (op.variant == 3 || (op.variant != 2 && op.variant != 4 && !warp_default))
     return launch2d_v2<T, N, MASS, LOCAL>(op, lambda, mu, x, y, ncomp, dot_xy,
                                           stream);
   if (op.variant != 2)

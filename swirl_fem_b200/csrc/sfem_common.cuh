@@ -44,14 +44,27 @@ extern std::atomic<int64_t> g_launch_count;
     }                                                                         \
   } while (0)
 
+// SM count of the CURRENT device (cached per device ordinal: a process may
+// drive several devices, and grids are sized from this).
 inline int num_sms() {
-  static int sms = [] {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess)
-      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n > 0 ? n : 148;
-  }();
-  return sms;
+  static int sms[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int& n = sms[dev & 63];
+  if (n == 0) {
+    int v = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n = v > 0 ? v : 148;
+  }
+  return n;
+}
+
+// Occupancy cache slot of the current device for a kernel's launcher
+// (`static int per_sm_dev[64]` in the launcher; 0 = not queried yet).
+inline int& per_device_slot(int (&slots)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return slots[dev & 63];
 }
 
 // ---- packed connectivity ------------------------------------------------------

@@ -197,7 +197,8 @@ int op_apply_halo_internal(const sfem_op* op, sfem_halo* halo, double lambda,
   }
   const size_t esz = d.dtype == SFEM_F64 ? 8 : 4;
   bool pdl = !prezeroed && (op->n_zero > 0 || dot_xy);
-  if (pdl && !pdl_enabled()) {
+  if (pdl && (!pdl_enabled() ||
+              esz * (size_t)op->n_zero > ((size_t)64 << 20))) {
     pdl = false;
     if (op->n_zero > 0)
       SFEM_CUDA_CHECK(cudaMemsetAsync(y, 0, esz * (size_t)op->n_zero, stream));

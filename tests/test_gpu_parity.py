@@ -361,12 +361,12 @@ def test_operator_apply_matches_oracle(case, dtype):
     oracle32 = dense.FESpace(refined.node_coords, refined.elements, n1d,
                              helpers.TNAME[GLL], q1d, helpers.TNAME[qt],
                              dtype=np.float32)
-  # 0: default specialised kernels (3-D three-mapping with bulk-async staging,
-  # 2-D warp-autonomous), 1: generic runtime-(N, Q) kernel, 2: v1 specialised
-  # kernels, 3 (2-D): the block-synchronous two-mapping kernel
+  # 0: default specialised kernels, 1: generic runtime-(N, Q) kernel, 2: v1
+  # specialised kernels, 3 / 4 (2-D): force the block-synchronous two-mapping /
+  # the warp-autonomous kernel (the default picks one of them by N)
   variants = [0, 1, 2] if qt == GLL and q1d == n1d and ndim > 1 else [0]
   if len(variants) > 1 and ndim == 2:
-    variants.append(3)
+    variants += [3, 4]
   for lam, mu in ((0.0, 1.0), (1.0, 0.0), (1833.3, 0.7)):
     want = oracle.apply(u, lam=lam, mu=mu, interior_mask=interior)
     if oracle32 is not None:
@@ -905,6 +905,24 @@ def test_multi_gpu_partitioned_parity():
          '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
          '--master-port', '29533', os.path.join(root, 'tools',
                                                 'check_multi_gpu.py')]
+  proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+  assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+
+
+def test_multi_gpu_communication_contracts_nccl():
+  """Crystal router, pscan / preduce and the general-partition halo with CUDA
+  tensors over NCCL + peer memory, 2 ranks (needs >= 2 GPUs; the same checks
+  run over gloo in tests/test_distributed_cpu.py)."""
+  import os
+  import subprocess
+  import sys
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs at least 2 GPUs')
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+         '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+         '--master-port', '29537', os.path.join(root, 'tools',
+                                                'check_comm_nccl.py')]
   proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
   assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
 
