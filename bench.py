@@ -502,6 +502,12 @@ def run_ours(args):
     torch.cuda.synchronize()
     apply_ms.append(a.elapsed_time(b))
   apply_ms = float(np.mean(apply_ms))
+  # every rank's own numbers (the job runs at the pace of its slowest GPU)
+  per_rank = None
+  if world > 1:
+    mine_ms = (float(ev[0].elapsed_time(ev[-1])) / args.steps, apply_ms)
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, mine_ms)
   abytes = algorithmic_bytes(mesh.num_nodes, num_local_nodes, args.dim, esz)
   peak, peak_src = measured_peak_gbs()
   achieved = abytes / (apply_ms * 1e-3) / 1e9
@@ -676,6 +682,10 @@ def run_ours(args):
             'local_dofs_rank0': mesh.num_nodes,
             'elements_rank0': mesh.num_elements,
             'geometric_factors_gb_per_rank': op.geom.numel() * esz / 1e9,
+            'per_rank_ms': None if per_rank is None else {
+                'step_with_exchange': [round(a, 5) for a, _ in per_rank],
+                'local_kernel_without_exchange': [round(b, 5)
+                                                  for _, b in per_rank]},
             'setup_s': t_setup,
         },
         'clocks': clocks,
