@@ -244,6 +244,30 @@ int sfem_op_diag(const sfem_op* op, double lambda, double mu, void* diag,
  * available), 1 = force the generic runtime-(N,Q) kernel.  For tests.       */
 int sfem_op_set_variant(sfem_op* op, int32_t variant);
 
+/* Lazy zero fill of y's shared-dof prefix for the 3-D fused apply (one
+ * component, not partitioned).  The scatter of poisson.py:141-146 /
+ * gather_scatter.py:130-133 is a zero-initialised scatter-add; the kernel
+ * accumulates shared dofs with RED, so they must be zero first.  Instead of
+ * filling the whole prefix before the launch (3 DRAM accesses per shared dof:
+ * zeros written, evicted, re-fetched by the first RED), the CTA steps of
+ * element chunk c zero the dofs that chunk c + lookahead touches FIRST, while
+ * they are still L2-resident when the REDs arrive.
+ *   sfem_op_step_elems: elements per CTA step (granularity of `duty`).
+ *   duty (device, 2 x int4 per step): four {start, len} node ranges the step
+ *     zeroes; eager (device int2[num_eager]): ranges zeroed before the launch
+ *     (first touched by chunks < lookahead, or by no element at all).  The
+ *     ranges over all steps and `eager` must cover [0, n_zero) exactly once;
+ *     the step that zeroes a dof must belong to chunk(first touch) -
+ *     lookahead.  chunk_steps: CTA steps per chunk.  Tables are retained (not
+ *     copied); duty = NULL switches back to the eager fill. */
+int32_t sfem_op_step_elems(const sfem_op* op);
+/* Length of the prefix y[0 .. n) that holds every dof touched by more than one
+ * element (or by none): what an apply zeroes before accumulating. */
+int64_t sfem_op_num_zero(const sfem_op* op);
+int sfem_op_set_lazy_zero(sfem_op* op, const void* duty, int64_t num_steps,
+                          const void* eager, int32_t num_eager,
+                          int32_t chunk_steps, int32_t lookahead);
+
 /* ------------------------------------------------------------------------ */
 /* Peer-memory halo exchange (partitioned QQ^T over NVLink P2P stores)       */
 /* ------------------------------------------------------------------------ */

@@ -76,6 +76,105 @@ class FusedOperator:
     self.handle = handle
     self.num_nodes = mesh.num_nodes
     self.ndim = mesh.ndim
+    self._lazy = None
+    # Large 3-D meshes: zero y's shared-dof prefix lazily inside the apply
+    # kernel (SFEM_LAZY_ZERO=0 keeps the eager fill, =1 forces the tables).
+    import os  # pylint: disable=g-import-not-at-top
+    mode = os.environ.get('SFEM_LAZY_ZERO', 'auto')
+    if mode != '0' and mesh.ndim == 3 and interp.collocated:
+      nz = int(lib.sfem_op_num_zero(self.handle))
+      if mode == '1' or nz * esz >= (64 << 20):
+        self.enable_lazy_zero(
+            chunk_elems=int(os.environ.get('SFEM_LAZY_CHUNK', 512)),
+            lookahead=int(os.environ.get('SFEM_LAZY_AHEAD', 2)))
+
+  def enable_lazy_zero(self, chunk_elems: int = 512, lookahead: int = 2) -> bool:
+    """Builds the tables of the lazy zero fill (`sfem_op_set_lazy_zero`).
+
+    The elements are cut into chunks of ~`chunk_elems` (a whole number of CTA
+    steps); every shared dof belongs to the chunk that touches it first, and
+    the CTA steps of chunk c zero the dofs of chunk c + `lookahead` (each step
+    an equal share, at most four contiguous id ranges).  Index arithmetic only
+    (torch on the device, set-up time).  Returns False -- and leaves the eager
+    fill in place -- when the numbering is too fragmented for four ranges per
+    step or the mesh has too few chunks.
+    """
+    lib = _lib.lib()
+    epb = int(lib.sfem_op_step_elems(self.handle))
+    nz = int(lib.sfem_op_num_zero(self.handle))
+    mesh = self.mesh
+    E, n = mesh.num_elements, mesh.num_nodes_per_element
+    if epb <= 0 or nz <= 0:
+      return False
+    S = max(1, int(round(chunk_elems / epb)))
+    num_steps = -(-E // epb)
+    num_chunks = -(-num_steps // S)
+    if num_chunks < lookahead + 2 or self.num_nodes >= 2 ** 31:
+      return False
+    dev = mesh.device
+    big = torch.iinfo(torch.int32).max
+    flat = mesh.elements.reshape(-1).long()
+    chunk = (torch.arange(E, device=dev) // (S * epb)).repeat_interleave(n)
+    sel = (flat >= 0) & (flat < nz)
+    first = torch.full((nz,), big, dtype=torch.int64, device=dev)
+    first.scatter_reduce_(0, flat[sel], chunk[sel], 'amin', include_self=True)
+    del flat, chunk, sel
+    # the chunk whose steps zero the dof (-1: before the launch)
+    target = torch.where(first == big, torch.full_like(first, -1),
+                         (first - lookahead).clamp(min=-1))
+    del first
+    order = torch.argsort(target, stable=True)        # ids by target, then id
+    st = target[order]
+    new_run = torch.ones(nz, dtype=torch.bool, device=dev)
+    new_run[1:] = (order[1:] != order[:-1] + 1) | (st[1:] != st[:-1])
+    run_pos = torch.nonzero(new_run).reshape(-1)       # position of run starts
+    run_id = order[run_pos]
+    run_end = torch.cat([run_pos[1:], torch.tensor([nz], device=dev)])
+    run_chunk = st[run_pos]
+    # eager ranges
+    eager_sel = run_chunk < 0
+    eager = torch.stack([run_id[eager_sel], (run_end - run_pos)[eager_sel]],
+                        dim=1).to(torch.int32).contiguous()
+    if eager.shape[0] > (1 << 20):
+      return False
+    # positions [p0, p1) of every duty chunk in `order`
+    bounds = torch.searchsorted(
+        st, torch.arange(num_chunks + 1, device=dev, dtype=st.dtype))
+    steps = torch.arange(num_steps, device=dev)
+    t = steps // S
+    j = steps - t * S
+    p0, p1 = bounds[t], bounds[t + 1]
+    share = (p1 - p0 + S - 1) // S
+    lo = torch.minimum(p0 + j * share, p1)
+    hi = torch.minimum(lo + share, p1)
+    has = hi > lo
+    r0 = torch.searchsorted(run_pos, lo, right=True) - 1
+    r1 = torch.searchsorted(run_pos, (hi - 1).clamp(min=0), right=True) - 1
+    nruns = torch.where(has, r1 - r0 + 1, torch.zeros_like(r0))
+    if int(nruns.max()) > 4:
+      return False
+    duty = torch.zeros((num_steps, 8), dtype=torch.int32, device=dev)
+    last_run = run_pos.numel() - 1
+    for k in range(4):
+      r = (r0 + k).clamp(max=last_run)
+      use = has & (r0 + k <= r1)
+      a = torch.maximum(lo, run_pos[r])
+      b = torch.minimum(hi, run_end[r])
+      duty[:, 2 * k] = torch.where(use, run_id[r] + (a - run_pos[r]),
+                                   torch.zeros_like(a)).to(torch.int32)
+      duty[:, 2 * k + 1] = torch.where(use, b - a,
+                                       torch.zeros_like(a)).to(torch.int32)
+    duty = duty.contiguous()
+    _lib._check(lib.sfem_op_set_lazy_zero(
+        self.handle, _lib.ptr(duty), num_steps, _lib.ptr(eager),
+        int(eager.shape[0]), S, int(lookahead)), 'sfem_op_set_lazy_zero')
+    self._lazy = (duty, eager)   # the C side retains these pointers
+    return True
+
+  def disable_lazy_zero(self):
+    _lib._check(_lib.lib().sfem_op_set_lazy_zero(self.handle, None, 0, None, 0,
+                                                 1, 1), 'sfem_op_set_lazy_zero')
+    self._lazy = None
 
   def __del__(self):
     h = getattr(self, 'handle', None)

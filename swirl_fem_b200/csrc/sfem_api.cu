@@ -35,6 +35,8 @@ int launch_diag_generic(const sfem_op&, double, double, void*, cudaStream_t);
 template <typename T, int DIM>
 int launch_apply_colloc_dim(const sfem_op&, double, double, const void*, void*,
                             int, bool, double*, cudaStream_t);
+template <typename T>
+int step_elems_3d(int n1d, bool mass);
 int pack_connectivity(const sfem_space_desc& desc, int n,
                       const uint8_t* dirichlet, uint32_t* conn,
                       int64_t* n_zero, cudaStream_t stream);
@@ -152,8 +154,11 @@ int op_apply_internal(const sfem_op* op, double lambda, double mu,
                    d.dim == 3 && d.n1d <= 16 && (op->n_zero > 0 || dot_xy) &&
                    esz * (size_t)op->n_zero * ncomp <= ((size_t)64 << 20);
   sfem_op sub = *op;
+  sub.prezeroed = prezeroed;
   if (prezeroed) {
     sub.pdl = false;
+  } else if (lazy_zero_applicable(sub, ncomp)) {
+    sub.pdl = false;  // the 3-D launcher fills (lazily) itself
   } else if (pdl) {
     int rc = launch_zero_fill(y, esz * (size_t)op->n_zero * ncomp, dot_xy,
                               stream, &sub.pdl);
@@ -322,6 +327,47 @@ void sfem_op_destroy(sfem_op* op) {
   if (!op) return;
   sfem::space_base_free(&op->base);
   delete op;
+}
+
+int64_t sfem_op_num_zero(const sfem_op* op) { return op ? op->n_zero : -1; }
+
+int32_t sfem_op_step_elems(const sfem_op* op) {
+  using namespace sfem;
+  if (!op) return 0;
+  const sfem_space_desc& d = op->base.desc;
+  if (d.dim != 3 || !d.collocated || d.n1d > 16) return 0;
+  return d.dtype == SFEM_F64 ? step_elems_3d<double>(d.n1d, op->with_mass != 0)
+                             : step_elems_3d<float>(d.n1d, op->with_mass != 0);
+}
+
+int sfem_op_set_lazy_zero(sfem_op* op, const void* duty, int64_t num_steps,
+                          const void* eager, int32_t num_eager,
+                          int32_t chunk_steps, int32_t lookahead) {
+  using namespace sfem;
+  SFEM_REQUIRE(op, "null argument");
+  if (duty == nullptr) {  // switch off
+    op->lazy_duty = nullptr;
+    return SFEM_OK;
+  }
+  const int epb = sfem_op_step_elems(op);
+  SFEM_REQUIRE(epb > 0, "lazy zero fill: 3-D collocated operators only");
+  const int64_t E = op->base.desc.num_elements;
+  SFEM_REQUIRE(num_steps == (E + epb - 1) / epb,
+               "lazy zero fill: duty table does not match the step count");
+  SFEM_REQUIRE(chunk_steps >= 1 && lookahead >= 1 && num_eager >= 0 &&
+                   (num_eager == 0 || eager != nullptr),
+               "lazy zero fill: bad chunking");
+  SFEM_REQUIRE(op->base.desc.num_nodes < ((int64_t)1 << 31),
+               "lazy zero fill: node ids must fit 31 bits");
+  op->lazy_duty = (const int4*)duty;
+  op->lazy_eager = (const int2*)eager;
+  op->lazy_num_eager = num_eager;
+  op->lazy_num_steps = num_steps;
+  op->lazy_epb = epb;
+  op->lazy_chunk_steps = chunk_steps;
+  op->lazy_lookahead = lookahead;
+  op->lazy_num_chunks = (int)((num_steps + chunk_steps - 1) / chunk_steps);
+  return SFEM_OK;
 }
 
 int sfem_op_set_variant(sfem_op* op, int32_t variant) {

@@ -245,8 +245,12 @@ __device__ __forceinline__ void bulk_copy_g2s_evict_first(void* smem_dst,
 //          of the next element's connectivity, a DRAM load issued only one
 //          barrier earlier);
 //   EVICT: factors staged with the evict-first copy above.
+// LAZY: y's shared-dof prefix is zeroed inside the kernel, a few chunks of
+// elements ahead of its first use (LazyDev, sfem_common.cuh); needs all CTAs
+// co-resident (cooperative launch) and ncomp == 1.
 template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH,
-          bool HALO = false, bool CONN2 = false, bool EVICT = false>
+          bool HALO = false, bool CONN2 = false, bool EVICT = false,
+          bool LAZY = false>
 __global__ void __launch_bounds__((Cfg3DV2<T, N, EPB, MINB, KCH>::threads),
                                   MINB)
 apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
@@ -254,7 +258,8 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
                   const T* __restrict__ gf, T lambda, T mu,
                   const T* __restrict__ x, T* __restrict__ y, int ncomp,
                   int64_t E, double* __restrict__ dot_xy,
-                  const __grid_constant__ HaloDev hd) {
+                  const __grid_constant__ HaloDev hd,
+                  const __grid_constant__ LazyDev lz) {
   using C = Cfg3DV2<T, N, EPB, MINB, KCH>;
   constexpr int P = C::P, n = C::n, epb = C::epb;
   constexpr int S0 = C::S0, R = C::R;
@@ -380,12 +385,39 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       nrc_c[k] = a1 ? ld_stream(conn + e1 * n + k * P + t) : kConnSentinel;
   }
 
+  // LAZY: this step's zero duty (loaded one step ahead) and the poll of the
+  // chunk counter this step's scatter depends on
+  int4 lz_d0 = make_int4(0, 0, 0, 0), lz_d1 = make_int4(0, 0, 0, 0);
+  if constexpr (LAZY) {
+    if (blk < nblocks) {
+      lz_d0 = __ldg(lz.duty + 2 * blk);
+      lz_d1 = __ldg(lz.duty + 2 * blk + 1);
+    }
+  }
+
   int buf = 0;
   for (; blk < nblocks; blk += gridDim.x, buf ^= 1) {
     T* sU = sU0 + buf * C::tile;
     T* sUn = sU0 + (buf ^ 1) * C::tile;
     // ---- pipeline: next element's factors -> L2, connectivity -> registers
     const int64_t blk_n = blk + gridDim.x;
+    // LAZY: issue the counter poll now, look at it before the scatter
+    unsigned lz_seen = 0, lz_need = 0;
+    const unsigned* lz_cnt = nullptr;
+    int4 lz_n0 = make_int4(0, 0, 0, 0), lz_n1 = make_int4(0, 0, 0, 0);
+    if constexpr (LAZY) {
+      // chunk c's first-touch dofs are zeroed by the S steps of chunk c - L
+      const int c_need = (int)(blk / lz.chunk_steps);
+      if (threadIdx.x == 0 && c_need >= lz.lookahead) {
+        lz_need = (unsigned)lz.chunk_steps;
+        lz_cnt = lz.counters + c_need;
+        lz_seen = ld_acquire_gpu(lz_cnt);
+      }
+      if (blk_n < nblocks) {
+        lz_n0 = __ldg(lz.duty + 2 * blk_n);
+        lz_n1 = __ldg(lz.duty + 2 * blk_n + 1);
+      }
+    }
     const int64_t e_n = blk_n * epb + slot;
     const bool active_n = lane_ok && blk_n < nblocks && e_n < E;
     uint32_t nrc[N];
@@ -449,6 +481,18 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     cp_async_wait_all();
     __syncthreads();
 
+    if constexpr (LAZY) {
+      // zero this step's share of the dofs that chunk (c + L) touches first
+      auto zero_range = [&](int start, int len) {
+        for (int i = threadIdx.x; i < len; i += blockDim.x)
+          y[start + i] = T(0);
+      };
+      zero_range(lz_d0.x, lz_d0.y);
+      zero_range(lz_d0.z, lz_d0.w);
+      zero_range(lz_d1.x, lz_d1.y);
+      zero_range(lz_d1.z, lz_d1.w);
+    }
+
     if (HALO) {
       if (hstate == kHIface && blk >= hd.n_if_blocks) {
         // every thread fenced its y updates at the end of the last interface
@@ -498,6 +542,18 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       for (int j = 0; j < N; ++j) sB[baseC + (SWZ ? (j ^ qs) : j)] = out[j];
     }
     __syncthreads();
+
+    if constexpr (LAZY) {
+      // every thread's zero stores precede the barrier above: count this step
+      // for the chunk it zeroed for (release)
+      if (threadIdx.x == 0) {
+        const int c_duty = (int)(blk / lz.chunk_steps) + lz.lookahead;
+        if (c_duty < lz.num_chunks) {
+          __threadfence();
+          atomicAdd(lz.counters + c_duty, 1u);
+        }
+      }
+    }
 
     if (HALO) {
       if (hstate == kHFenced && hticket == 0) {
@@ -609,6 +665,27 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
 #pragma unroll
       for (int j = 0; j < N; ++j) sB[baseC + (SWZ ? (j ^ qs) : j)] = out[j];
     }
+    if constexpr (LAZY) {
+      // the dofs this step scatters into have been zeroed once every step of
+      // chunk (c - L) has counted itself (normally long ago: no spin)
+      if (threadIdx.x == 0 && lz_cnt != nullptr && lz_seen < lz_need) {
+        // bounded (~2 s): inconsistent tables must not hang the device; the
+        // sticky word after the counters records it
+        uint64_t t0 = 0;
+        unsigned spins = 0;
+        while ((lz_seen = ld_acquire_gpu(lz_cnt)) < lz_need) {
+          if ((++spins & 1023u) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 2000000000ull) {
+              atomicExch(lz.counters + lz.num_chunks, 1u);
+              break;
+            }
+          }
+        }
+      }
+    }
     __syncthreads();
 
     // ---- phase 5 (mapping A): sum the three parts, scatter
@@ -645,6 +722,10 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     // in-flight cp.async targets the OTHER u tile).
     e = e_n;
     active = active_n;
+    if constexpr (LAZY) {
+      lz_d0 = lz_n0;
+      lz_d1 = lz_n1;
+    }
 #pragma unroll
     for (int k = 0; k < N; ++k) rc[k] = nrc[k];
     if (HALO && hstate == kHIface && blk_n >= hd.n_if_blocks) __threadfence();
@@ -698,8 +779,26 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
   }
 }
 
+// Pre-launch part of the lazy zero fill: the ranges chunks 0 .. L-1 touch first
+// (and dofs no element touches), the chunk counters and the dot accumulator.
+template <typename T>
+__global__ void __launch_bounds__(256)
+zero_ranges_kernel(T* __restrict__ y, const int2* __restrict__ ranges,
+                   int num_ranges, unsigned* __restrict__ counters,
+                   int num_counters, double* __restrict__ dot_xy) {
+  for (int r = blockIdx.x; r < num_ranges; r += gridDim.x) {
+    const int2 rg = __ldg(ranges + r);
+    for (int i = threadIdx.x; i < rg.y; i += blockDim.x) y[rg.x + i] = T(0);
+  }
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < num_counters; i += blockDim.x) counters[i] = 0u;
+    if (threadIdx.x == 0 && dot_xy) *dot_xy = 0.0;
+  }
+}
+
 template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH,
-          bool HALO = false, bool CONN2 = false, bool EVICT = false>
+          bool HALO = false, bool CONN2 = false, bool EVICT = false,
+          bool LAZY = false>
 int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
                     void* y, int ncomp, double* dot_xy, cudaStream_t stream) {
   using C = Cfg3DV2<T, N, EPB, MINB, KCH>;
@@ -709,8 +808,8 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
       ((size_t)C::stage_off(C::epb) +
        (KCH == 0 ? (size_t)C::epb * (MASS ? 7 : 6) * C::n : 0)) *
       sizeof(T);
-  auto kernel =
-      apply3d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB, KCH, HALO, CONN2, EVICT>;
+  auto kernel = apply3d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB, KCH, HALO, CONN2,
+                                  EVICT, LAZY>;
   static int per_sm_dev[64] = {};
   int& per_sm = per_device_slot(per_sm_dev);
   if (per_sm == 0) {
@@ -753,10 +852,61 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
     hd = f;
     hd.n_if_blocks = (hd.n_if_blocks + C::epb - 1) / C::epb;
   }
+  LazyDev lz{};
+  if constexpr (LAZY) {
+    // eager part + counters, then the kernel as a cooperative launch (its
+    // chunk counters need every CTA resident); any failure falls back to the
+    // eager fill + the ordinary kernel
+    static_assert(!HALO && !LOCAL, "lazy zero fill: plain global apply only");
+    // + 1: sticky "a wait timed out" word
+    const size_t cbytes = sizeof(unsigned) * ((size_t)op.lazy_num_chunks + 1);
+    unsigned* counters = nullptr;
+    bool ok = op.lazy_epb == EPB &&
+              cudaMallocAsync((void**)&counters, cbytes, stream) == cudaSuccess;
+    if (ok) {
+      int zb = op.lazy_num_eager < 1 ? 1 : op.lazy_num_eager;
+      if (zb > num_sms() * 4) zb = num_sms() * 4;
+      zero_ranges_kernel<T><<<zb, 256, 0, stream>>>(
+          (T*)y, op.lazy_eager, op.lazy_num_eager, counters,
+          op.lazy_num_chunks + 1, dot_xy);
+      g_launch_count.fetch_add(1, std::memory_order_relaxed);
+      lz.duty = op.lazy_duty;
+      lz.counters = counters;
+      lz.chunk_steps = op.lazy_chunk_steps;
+      lz.lookahead = op.lazy_lookahead;
+      lz.num_chunks = op.lazy_num_chunks;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(C::threads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      const cudaError_t e = cudaLaunchKernelEx(
+          &cfg, kernel, dm, (const uint32_t*)op.conn, (const T*)op.geom,
+          (T)lambda, (T)mu, (const T*)x, (T*)y, ncomp, E, dot_xy, hd, lz);
+      cudaFreeAsync(counters, stream);
+      if (e == cudaSuccess) {
+        SFEM_LAUNCH_CHECK();
+        return SFEM_OK;
+      }
+    }
+    cudaGetLastError();  // clear; fall back to the eager fill
+    const size_t esz = sizeof(T);
+    if (op.n_zero > 0)
+      SFEM_CUDA_CHECK(cudaMemsetAsync(y, 0, esz * (size_t)op.n_zero, stream));
+    if (dot_xy)
+      SFEM_CUDA_CHECK(cudaMemsetAsync(dot_xy, 0, sizeof(double), stream));
+    return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, MINB, KCH, HALO, CONN2, EVICT,
+                           false>(op, lambda, mu, x, y, ncomp, dot_xy, stream);
+  }
   SFEM_CUDA_CHECK(launch_maybe_pdl(
       op.pdl, kernel, grid, dim3(C::threads), smem, stream, dm, op.conn,
       (const T*)op.geom, (T)lambda, (T)mu, (const T*)x, (T*)y, ncomp, E,
-      dot_xy, hd));
+      dot_xy, hd, lz));
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }
@@ -890,9 +1040,22 @@ int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
   }
 #endif
   using Tn = Tune3D<T, N>;
+  if constexpr (!LOCAL) {
+    if (lazy_zero_applicable(op, ncomp))
+      return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
+                             Tn::conn2, Tn::evict, true>(op, lambda, mu, x, y,
+                                                         ncomp, dot_xy, stream);
+  }
   return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
                          Tn::conn2 && !LOCAL, Tn::evict>(
       op, lambda, mu, x, y, ncomp, dot_xy, stream);
+}
+
+// Elements per CTA step of the default 3-D configuration (the granularity of
+// the lazy zero fill's duty table).
+template <typename T, int N>
+int step_elems3d(bool mass) {
+  return mass ? default_epb3d<T, N, true>() : default_epb3d<T, N, false>();
 }
 
 // Default configuration of launch3d_v2 with the halo push fused in.

@@ -383,6 +383,27 @@ __device__ __forceinline__ bool scalar_allreduce_warp(const ScalarDev& sx,
   return ok;
 }
 
+// ---- lazy zero fill of y's shared-dof prefix (3-D fused apply) ------------------
+// The shared dofs of y are accumulated with RED, so they must be zero first.
+// Filling the whole prefix before the launch costs three DRAM accesses per
+// shared dof instead of one: the zeros are written, evicted (the prefix is
+// 320 MB at 108 M dofs, L2 is 126 MB), fetched again by the first RED and
+// written back.  Lazily, the CTA steps of element chunk c zero exactly the
+// dofs that chunk c + L touches FIRST, a few tens of MB of traffic ahead of
+// their first RED: the lines are still in L2 when the REDs arrive and go to
+// DRAM once.  `duty[step]` (host-built, sfem_op_set_lazy_zero) lists up to four
+// node ranges per CTA step; `counters[c]` counts the steps that finished their
+// share of chunk c; a step scatters only after counters[chunk of its last
+// element] reached the number of steps of chunk c - L (pipelined poll, a spin
+// only if a CTA runs more than L chunks ahead of the slowest one).
+struct LazyDev {
+  const int4* duty;     // (2 * num_steps): ranges {start0, len0, start1, len1} x 2
+  unsigned* counters;   // (num_chunks), zeroed before the launch
+  int chunk_steps;      // S: chunk of a CTA step = step / S
+  int lookahead;        // L
+  int num_chunks;
+};
+
 // symmetric index of (i,k), i<=k, in the packed d(d+1)/2 layout
 __host__ __device__ constexpr int sym_index(int dim, int i, int k) {
   return dim == 1 ? 0
@@ -447,6 +468,13 @@ struct sfem_op {
   // set on a shallow copy by the fused CG loop: y[0 .. n_zero) and the dot
   // accumulator were already zeroed by the previous cg_step_kernel
   bool prezeroed = false;
+  // lazy zero fill (sfem_op_set_lazy_zero): device tables owned by the caller
+  const int4* lazy_duty = nullptr;     // 2 x int4 per CTA step of `lazy_epb`
+  const int2* lazy_eager = nullptr;    // ranges zeroed before the launch
+  int lazy_num_eager = 0;
+  int64_t lazy_num_steps = 0;
+  int lazy_epb = 0, lazy_chunk_steps = 0, lazy_lookahead = 0;
+  int lazy_num_chunks = 0;
 };
 
 // Peer-memory all-reduce handle (sfem_halo.cu).
@@ -459,6 +487,14 @@ struct sfem_scalar_exchange {
 };
 
 namespace sfem {
+// True when the 3-D launcher zero-fills y itself (lazily, or eagerly as its own
+// fallback): the caller must not enqueue a fill.
+inline bool lazy_zero_applicable(const sfem_op& op, int ncomp) {
+  const sfem_space_desc& d = op.base.desc;
+  return op.lazy_duty != nullptr && ncomp == 1 && op.variant == 0 &&
+         d.collocated && d.dim == 3 && d.n1d <= 16 && op.fuse == nullptr &&
+         !op.prezeroed;
+}
 inline ScalarDev scalar_view(const sfem_scalar_exchange* h) {
   ScalarDev d{};
   if (h) {

@@ -1,0 +1,42 @@
+#!/usr/bin/env bash
+# Round-2 GPU job 4 (1 GPU): lazy zero fill -- tests, on/off and chunking at
+# ne=68, DRAM traffic of the kernel (ncu --set full), launch list.
+set -u
+mkdir -p gpurun_out
+O=gpurun_out
+timeout 600 python -m pytest tests -m gpu -q -p no:cacheprovider --tb=short -k "lazy" > $O/r2_run4_pytest_lazy.log 2>&1
+tail -3 $O/r2_run4_pytest_lazy.log
+timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider --tb=short > $O/r2_run4_pytest.log 2>&1
+tail -3 $O/r2_run4_pytest.log
+B="python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline --no-extra --no-parity --cg-iters 30"
+SFEM_LAZY_ZERO=0 timeout 600 $B > $O/r2_lazy_off.json 2> $O/r2_lazy_off.err
+for cfg in "512 2" "256 2" "1024 2" "512 1" "1024 1" "2048 1" "512 3"; do
+  set -- $cfg
+  SFEM_LAZY_CHUNK=$1 SFEM_LAZY_AHEAD=$2 timeout 600 $B > $O/r2_lazy_c$1_a$2.json 2> $O/r2_lazy_c$1_a$2.err
+done
+for f in $O/r2_lazy_*.json; do python - "$f" <<'PY'
+import json,sys
+try:
+  d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+  print(sys.argv[1], 'apply %.2f GDOF/s %.4f ms frac %.3f | cg %.4f ms/it frac %.3f'%(d['value'],d['ms_per_step'],d['roofline']['frac'],d['cg']['ms_per_iteration'],d['cg']['roofline_frac']))
+except Exception as e: print(sys.argv[1],'ERR',e)
+PY
+done
+# DRAM traffic of one launch of the (lazy) kernel
+timeout 900 ncu --set full --clock-control none -k regex:apply3d_v2 -s 8 -c 1 -o $O/prof_lazy -f \
+  python bench.py --steps 4 --warmup 5 --no-e2e --no-cpu-baseline --no-extra --no-parity --cg-iters 0 > $O/r2_ncu_lazy.log 2>&1
+if [ -f $O/prof_lazy.ncu-rep ]; then
+  ncu -i $O/prof_lazy.ncu-rep --page raw --csv > $O/prof_lazy_raw.csv 2>/dev/null
+  python tools/ncu_summary.py $O/prof_lazy_raw.csv > $O/r2_ncu_apply3d_ne68_lazy.txt
+  ncu -i $O/prof_lazy.ncu-rep --page source --csv 2>/dev/null | gzip > $O/r2_source_apply3d_ne68_lazy.csv.gz
+  rm -f $O/prof_lazy_raw.csv $O/prof_lazy.ncu-rep
+fi
+SFEM_LAZY_ZERO=0 timeout 900 ncu --set full --clock-control none -k regex:apply3d_v2 -s 8 -c 1 -o $O/prof_eager -f \
+  python bench.py --steps 4 --warmup 5 --no-e2e --no-cpu-baseline --no-extra --no-parity --cg-iters 0 > $O/r2_ncu_eager.log 2>&1
+if [ -f $O/prof_eager.ncu-rep ]; then
+  ncu -i $O/prof_eager.ncu-rep --page raw --csv > $O/prof_eager_raw.csv 2>/dev/null
+  python tools/ncu_summary.py $O/prof_eager_raw.csv > $O/r2_ncu_apply3d_ne68_eager.txt
+  rm -f $O/prof_eager_raw.csv $O/prof_eager.ncu-rep
+fi
+du -sh $O
+echo done
