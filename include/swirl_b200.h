@@ -252,21 +252,24 @@ int sfem_op_set_variant(sfem_op* op, int32_t variant);
  * zeros written, evicted, re-fetched by the first RED), the CTA steps of
  * element chunk c zero the dofs that chunk c + lookahead touches FIRST, while
  * they are still L2-resident when the REDs arrive.
- *   sfem_op_step_elems: elements per CTA step (granularity of `duty`).
- *   duty (device, 2 x int4 per step): four {start, len} node ranges the step
- *     zeroes; eager (device int2[num_eager]): ranges zeroed before the launch
- *     (first touched by chunks < lookahead, or by no element at all).  The
- *     ranges over all steps and `eager` must cover [0, n_zero) exactly once;
- *     the step that zeroes a dof must belong to chunk(first touch) -
- *     lookahead.  chunk_steps: CTA steps per chunk.  Tables are retained (not
- *     copied); duty = NULL switches back to the eager fill. */
+ *   sfem_op_step_elems: elements per CTA step.  A chunk is `chunk_steps`
+ *     consecutive steps; every `duty_every`-th step (duty_every divides
+ *     chunk_steps) is a duty step.
+ *   pieces (device int2[]): {start, len <= 128} node ranges.  The first
+ *     `num_eager` are zeroed before the launch (dofs first touched by chunks
+ *     < lookahead, or by no element); duty step q = step / duty_every owns
+ *     pieces [duty_ptr[q], duty_ptr[q + 1]) (device int32[num_duty + 1]) and
+ *     must belong to chunk(first touch of those dofs) - lookahead.  All pieces
+ *     together cover [0, sfem_op_num_zero) exactly once.  Tables are retained
+ *     (not copied); duty_ptr = NULL switches back to the eager fill. */
 int32_t sfem_op_step_elems(const sfem_op* op);
 /* Length of the prefix y[0 .. n) that holds every dof touched by more than one
  * element (or by none): what an apply zeroes before accumulating. */
 int64_t sfem_op_num_zero(const sfem_op* op);
-int sfem_op_set_lazy_zero(sfem_op* op, const void* duty, int64_t num_steps,
-                          const void* eager, int32_t num_eager,
-                          int32_t chunk_steps, int32_t lookahead);
+int sfem_op_set_lazy_zero(sfem_op* op, const void* pieces, int32_t num_eager,
+                          const int32_t* duty_ptr, int64_t num_duty,
+                          int32_t chunk_steps, int32_t duty_every,
+                          int32_t lookahead);
 
 /* ------------------------------------------------------------------------ */
 /* Peer-memory halo exchange (partitioned QQ^T over NVLink P2P stores)       */

@@ -86,94 +86,39 @@ class FusedOperator:
       if mode == '1' or nz * esz >= (64 << 20):
         self.enable_lazy_zero(
             chunk_elems=int(os.environ.get('SFEM_LAZY_CHUNK', 512)),
-            lookahead=int(os.environ.get('SFEM_LAZY_AHEAD', 2)))
+            lookahead=int(os.environ.get('SFEM_LAZY_AHEAD', 2)),
+            duty_every=int(os.environ.get('SFEM_LAZY_DUTY', 8)))
 
-  def enable_lazy_zero(self, chunk_elems: int = 512, lookahead: int = 2) -> bool:
+  def enable_lazy_zero(self, chunk_elems: int = 512, lookahead: int = 2,
+                       duty_every: int = 8, piece: int = 128) -> bool:
     """Builds the tables of the lazy zero fill (`sfem_op_set_lazy_zero`).
 
     The elements are cut into chunks of ~`chunk_elems` (a whole number of CTA
-    steps); every shared dof belongs to the chunk that touches it first, and
-    the CTA steps of chunk c zero the dofs of chunk c + `lookahead` (each step
-    an equal share, at most four contiguous id ranges).  Index arithmetic only
-    (torch on the device, set-up time).  Returns False -- and leaves the eager
-    fill in place -- when the numbering is too fragmented for four ranges per
-    step or the mesh has too few chunks.
+    steps, a multiple of `duty_every`); every shared dof belongs to the chunk
+    that touches it first, and the duty steps (every `duty_every`-th CTA step)
+    of chunk c zero the dofs of chunk c + `lookahead`, each an equal share
+    cut into pieces of at most `piece` consecutive dofs.  Index arithmetic
+    only (torch on the device, set-up time).  Returns False -- and leaves the
+    eager fill in place -- when the mesh has too few chunks.
     """
-    lib = _lib.lib()
-    epb = int(lib.sfem_op_step_elems(self.handle))
-    nz = int(lib.sfem_op_num_zero(self.handle))
-    mesh = self.mesh
-    E, n = mesh.num_elements, mesh.num_nodes_per_element
-    if epb <= 0 or nz <= 0:
+    tables = lazy_zero_tables(
+        self.mesh.elements, self.num_nodes,
+        int(_lib.lib().sfem_op_num_zero(self.handle)),
+        int(_lib.lib().sfem_op_step_elems(self.handle)), chunk_elems,
+        lookahead, duty_every, piece)
+    if tables is None:
       return False
-    S = max(1, int(round(chunk_elems / epb)))
-    num_steps = -(-E // epb)
-    num_chunks = -(-num_steps // S)
-    if num_chunks < lookahead + 2 or self.num_nodes >= 2 ** 31:
-      return False
-    dev = mesh.device
-    big = torch.iinfo(torch.int32).max
-    flat = mesh.elements.reshape(-1).long()
-    chunk = (torch.arange(E, device=dev) // (S * epb)).repeat_interleave(n)
-    sel = (flat >= 0) & (flat < nz)
-    first = torch.full((nz,), big, dtype=torch.int64, device=dev)
-    first.scatter_reduce_(0, flat[sel], chunk[sel], 'amin', include_self=True)
-    del flat, chunk, sel
-    # the chunk whose steps zero the dof (-1: before the launch)
-    target = torch.where(first == big, torch.full_like(first, -1),
-                         (first - lookahead).clamp(min=-1))
-    del first
-    order = torch.argsort(target, stable=True)        # ids by target, then id
-    st = target[order]
-    new_run = torch.ones(nz, dtype=torch.bool, device=dev)
-    new_run[1:] = (order[1:] != order[:-1] + 1) | (st[1:] != st[:-1])
-    run_pos = torch.nonzero(new_run).reshape(-1)       # position of run starts
-    run_id = order[run_pos]
-    run_end = torch.cat([run_pos[1:], torch.tensor([nz], device=dev)])
-    run_chunk = st[run_pos]
-    # eager ranges
-    eager_sel = run_chunk < 0
-    eager = torch.stack([run_id[eager_sel], (run_end - run_pos)[eager_sel]],
-                        dim=1).to(torch.int32).contiguous()
-    if eager.shape[0] > (1 << 20):
-      return False
-    # positions [p0, p1) of every duty chunk in `order`
-    bounds = torch.searchsorted(
-        st, torch.arange(num_chunks + 1, device=dev, dtype=st.dtype))
-    steps = torch.arange(num_steps, device=dev)
-    t = steps // S
-    j = steps - t * S
-    p0, p1 = bounds[t], bounds[t + 1]
-    share = (p1 - p0 + S - 1) // S
-    lo = torch.minimum(p0 + j * share, p1)
-    hi = torch.minimum(lo + share, p1)
-    has = hi > lo
-    r0 = torch.searchsorted(run_pos, lo, right=True) - 1
-    r1 = torch.searchsorted(run_pos, (hi - 1).clamp(min=0), right=True) - 1
-    nruns = torch.where(has, r1 - r0 + 1, torch.zeros_like(r0))
-    if int(nruns.max()) > 4:
-      return False
-    duty = torch.zeros((num_steps, 8), dtype=torch.int32, device=dev)
-    last_run = run_pos.numel() - 1
-    for k in range(4):
-      r = (r0 + k).clamp(max=last_run)
-      use = has & (r0 + k <= r1)
-      a = torch.maximum(lo, run_pos[r])
-      b = torch.minimum(hi, run_end[r])
-      duty[:, 2 * k] = torch.where(use, run_id[r] + (a - run_pos[r]),
-                                   torch.zeros_like(a)).to(torch.int32)
-      duty[:, 2 * k + 1] = torch.where(use, b - a,
-                                       torch.zeros_like(a)).to(torch.int32)
-    duty = duty.contiguous()
-    _lib._check(lib.sfem_op_set_lazy_zero(
-        self.handle, _lib.ptr(duty), num_steps, _lib.ptr(eager),
-        int(eager.shape[0]), S, int(lookahead)), 'sfem_op_set_lazy_zero')
-    self._lazy = (duty, eager)   # the C side retains these pointers
+    pieces, num_eager, duty_ptr, chunk_steps = tables
+    _lib._check(_lib.lib().sfem_op_set_lazy_zero(
+        self.handle, _lib.ptr(pieces), int(num_eager), _lib.ptr(duty_ptr),
+        int(duty_ptr.numel() - 1), int(chunk_steps), int(duty_every),
+        int(lookahead)), 'sfem_op_set_lazy_zero')
+    self._lazy = (pieces, duty_ptr)   # the C side retains these pointers
     return True
 
   def disable_lazy_zero(self):
-    _lib._check(_lib.lib().sfem_op_set_lazy_zero(self.handle, None, 0, None, 0,
-                                                 1, 1), 'sfem_op_set_lazy_zero')
+    _lib._check(_lib.lib().sfem_op_set_lazy_zero(
+        self.handle, None, 0, None, 0, 1, 1, 1), 'sfem_op_set_lazy_zero')
     self._lazy = None
 
   def __del__(self):
@@ -314,6 +259,85 @@ class FusedOperator:
   def bind(self, lam: float = 0.0, mu: float = 1.0):
     """Returns the callable `A(u)` for these coefficients (for `linalg.cg`)."""
     return BoundOperator(self, lam, mu)
+
+
+def lazy_zero_tables(elements: torch.Tensor, num_nodes: int, num_zero: int,
+                     epb: int, chunk_elems: int, lookahead: int,
+                     duty_every: int, piece: int):
+  """Tables of the lazy zero fill (see `sfem_op_set_lazy_zero`).
+
+  Returns `(pieces int32 (P, 2), num_eager, duty_ptr int32 (num_duty + 1,),
+  chunk_steps)` or None when the mesh is too small.  Works on any device
+  (index arithmetic only)."""
+  E, n = int(elements.shape[0]), int(elements.shape[1])
+  if epb <= 0 or num_zero <= 0 or num_nodes >= 2 ** 31:
+    return None
+  kd = int(duty_every)
+  S = max(kd, int(round(chunk_elems / (epb * kd))) * kd)   # steps per chunk
+  num_steps = -(-E // epb)
+  num_chunks = -(-num_steps // S)
+  if num_chunks < lookahead + 2:
+    return None
+  dev = elements.device
+  big = torch.iinfo(torch.int32).max
+  nz = int(num_zero)
+  flat = elements.reshape(-1).long()
+  chunk = (torch.arange(E, device=dev) // (S * epb)).repeat_interleave(n)
+  sel = (flat >= 0) & (flat < nz)
+  first = torch.full((nz,), big, dtype=torch.int64, device=dev)
+  first.scatter_reduce_(0, flat[sel], chunk[sel], 'amin', include_self=True)
+  del flat, chunk, sel
+  # the chunk whose duty steps zero the dof (-1: before the launch)
+  target = torch.where(first == big, torch.full_like(first, -1),
+                       (first - lookahead).clamp(min=-1))
+  del first
+  order = torch.argsort(target, stable=True)          # ids by target, then id
+  st = target[order]
+  # position range of every target chunk in `order`; chunk t's range is split
+  # evenly over its S / kd duty steps; position nz never starts a share
+  dps = S // kd                                       # duty steps per chunk
+  num_duty = -(-num_steps // kd)
+  bounds = torch.searchsorted(
+      st, torch.arange(-1, num_chunks + 1, device=dev, dtype=st.dtype))
+  eager_end = int(bounds[1])                          # positions [0, eager_end)
+  q = torch.arange(num_duty, device=dev)
+  t = q // dps
+  j = q - t * dps
+  p0, p1 = bounds[t + 1], bounds[t + 2]
+  share = (p1 - p0 + dps - 1) // dps
+  lo = torch.minimum(p0 + j * share, p1)
+  hi = torch.minimum(lo + share, p1)
+  # cut points: run boundaries (id not consecutive), share boundaries, and
+  # every `piece` positions inside a segment
+  cut = torch.zeros(nz + 1, dtype=torch.bool, device=dev)
+  cut[0] = True
+  cut[nz] = True
+  cut[1:nz] = order[1:] != order[:-1] + 1
+  cut[lo] = True
+  cut[hi] = True
+  cut[eager_end] = True
+  seg_start = torch.nonzero(cut[:nz]).reshape(-1)
+  seg_end = torch.cat([seg_start[1:], torch.tensor([nz], device=dev)])
+  seg_len = seg_end - seg_start
+  npieces = (seg_len + piece - 1) // piece
+  seg_of_piece = torch.repeat_interleave(
+      torch.arange(seg_start.numel(), device=dev), npieces)
+  first_piece = torch.cumsum(npieces, 0) - npieces
+  k = torch.arange(seg_of_piece.numel(), device=dev) - first_piece[seg_of_piece]
+  pos = seg_start[seg_of_piece] + k * piece
+  plen = torch.minimum(torch.full_like(pos, piece),
+                       seg_end[seg_of_piece] - pos)
+  pieces = torch.stack([order[pos], plen], dim=1).to(torch.int32).contiguous()
+  # piece index of a position = number of pieces starting before it
+  num_eager = int(torch.searchsorted(pos, torch.tensor([eager_end], device=dev)))
+  duty_lo = torch.searchsorted(pos, lo)
+  duty_hi = torch.searchsorted(pos, hi)
+  duty_ptr = torch.cat([duty_lo, duty_hi[-1:]]).to(torch.int32).contiguous()
+  # shares are contiguous in position, so consecutive duty steps share their
+  # end points: duty_ptr[q + 1] == duty_hi[q] (empty shares collapse)
+  if not bool((duty_ptr[1:] == duty_hi.to(torch.int32)).all()):
+    return None
+  return pieces, num_eager, duty_ptr, S
 
 
 class HostPipeline:

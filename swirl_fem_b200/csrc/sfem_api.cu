@@ -340,31 +340,35 @@ int32_t sfem_op_step_elems(const sfem_op* op) {
                              : step_elems_3d<float>(d.n1d, op->with_mass != 0);
 }
 
-int sfem_op_set_lazy_zero(sfem_op* op, const void* duty, int64_t num_steps,
-                          const void* eager, int32_t num_eager,
-                          int32_t chunk_steps, int32_t lookahead) {
+int sfem_op_set_lazy_zero(sfem_op* op, const void* pieces, int32_t num_eager,
+                          const int32_t* duty_ptr, int64_t num_duty,
+                          int32_t chunk_steps, int32_t duty_every,
+                          int32_t lookahead) {
   using namespace sfem;
   SFEM_REQUIRE(op, "null argument");
-  if (duty == nullptr) {  // switch off
-    op->lazy_duty = nullptr;
+  if (duty_ptr == nullptr) {  // switch off
+    op->lazy_duty_ptr = nullptr;
     return SFEM_OK;
   }
   const int epb = sfem_op_step_elems(op);
   SFEM_REQUIRE(epb > 0, "lazy zero fill: 3-D collocated operators only");
   const int64_t E = op->base.desc.num_elements;
-  SFEM_REQUIRE(num_steps == (E + epb - 1) / epb,
-               "lazy zero fill: duty table does not match the step count");
-  SFEM_REQUIRE(chunk_steps >= 1 && lookahead >= 1 && num_eager >= 0 &&
-                   (num_eager == 0 || eager != nullptr),
+  const int64_t num_steps = (E + epb - 1) / epb;
+  SFEM_REQUIRE(pieces != nullptr && num_eager >= 0, "lazy zero fill: no pieces");
+  SFEM_REQUIRE(duty_every >= 1 && chunk_steps >= duty_every &&
+                   chunk_steps % duty_every == 0 && lookahead >= 1,
                "lazy zero fill: bad chunking");
+  SFEM_REQUIRE(num_duty == (num_steps + duty_every - 1) / duty_every,
+               "lazy zero fill: duty table does not match the step count");
   SFEM_REQUIRE(op->base.desc.num_nodes < ((int64_t)1 << 31),
                "lazy zero fill: node ids must fit 31 bits");
-  op->lazy_duty = (const int4*)duty;
-  op->lazy_eager = (const int2*)eager;
+  op->lazy_pieces = (const int2*)pieces;
+  op->lazy_duty_ptr = duty_ptr;
   op->lazy_num_eager = num_eager;
   op->lazy_num_steps = num_steps;
   op->lazy_epb = epb;
   op->lazy_chunk_steps = chunk_steps;
+  op->lazy_duty_every = duty_every;
   op->lazy_lookahead = lookahead;
   op->lazy_num_chunks = (int)((num_steps + chunk_steps - 1) / chunk_steps);
   return SFEM_OK;

@@ -385,13 +385,14 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       nrc_c[k] = a1 ? ld_stream(conn + e1 * n + k * P + t) : kConnSentinel;
   }
 
-  // LAZY: this step's zero duty (loaded one step ahead) and the poll of the
-  // chunk counter this step's scatter depends on
-  int4 lz_d0 = make_int4(0, 0, 0, 0), lz_d1 = make_int4(0, 0, 0, 0);
+  // LAZY: piece range of this step's zero duty (loaded one step ahead; empty
+  // unless this is a duty step)
+  int lz_b = 0, lz_e = 0;
   if constexpr (LAZY) {
-    if (blk < nblocks) {
-      lz_d0 = __ldg(lz.duty + 2 * blk);
-      lz_d1 = __ldg(lz.duty + 2 * blk + 1);
+    if (blk < nblocks && blk % lz.duty_every == 0) {
+      const int64_t q = blk / lz.duty_every;
+      lz_b = __ldg(lz.duty_ptr + q);
+      lz_e = __ldg(lz.duty_ptr + q + 1);
     }
   }
 
@@ -404,18 +405,19 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     // LAZY: issue the counter poll now, look at it before the scatter
     unsigned lz_seen = 0, lz_need = 0;
     const unsigned* lz_cnt = nullptr;
-    int4 lz_n0 = make_int4(0, 0, 0, 0), lz_n1 = make_int4(0, 0, 0, 0);
+    int lz_nb = 0, lz_ne = 0;
     if constexpr (LAZY) {
-      // chunk c's first-touch dofs are zeroed by the S steps of chunk c - L
+      // chunk c's first-touch dofs are zeroed by the duty steps of chunk c - L
       const int c_need = (int)(blk / lz.chunk_steps);
       if (threadIdx.x == 0 && c_need >= lz.lookahead) {
-        lz_need = (unsigned)lz.chunk_steps;
+        lz_need = (unsigned)(lz.chunk_steps / lz.duty_every);
         lz_cnt = lz.counters + c_need;
-        lz_seen = ld_acquire_gpu(lz_cnt);
+        lz_seen = ld_relaxed_gpu(lz_cnt);
       }
-      if (blk_n < nblocks) {
-        lz_n0 = __ldg(lz.duty + 2 * blk_n);
-        lz_n1 = __ldg(lz.duty + 2 * blk_n + 1);
+      if (blk_n < nblocks && blk_n % lz.duty_every == 0) {
+        const int64_t q = blk_n / lz.duty_every;
+        lz_nb = __ldg(lz.duty_ptr + q);
+        lz_ne = __ldg(lz.duty_ptr + q + 1);
       }
     }
     const int64_t e_n = blk_n * epb + slot;
@@ -482,15 +484,12 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     __syncthreads();
 
     if constexpr (LAZY) {
-      // zero this step's share of the dofs that chunk (c + L) touches first
-      auto zero_range = [&](int start, int len) {
-        for (int i = threadIdx.x; i < len; i += blockDim.x)
-          y[start + i] = T(0);
-      };
-      zero_range(lz_d0.x, lz_d0.y);
-      zero_range(lz_d0.z, lz_d0.w);
-      zero_range(lz_d1.x, lz_d1.y);
-      zero_range(lz_d1.z, lz_d1.w);
+      // duty step: zero this step's pieces (one piece of <= 128 dofs per
+      // thread) of the dofs that chunk (c + L) touches first
+      for (int r = lz_b + (int)threadIdx.x; r < lz_e; r += (int)blockDim.x) {
+        const int2 pc = __ldg(lz.pieces + r);
+        for (int i = 0; i < pc.y; ++i) y[pc.x + i] = T(0);
+      }
     }
 
     if (HALO) {
@@ -546,11 +545,11 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     if constexpr (LAZY) {
       // every thread's zero stores precede the barrier above: count this step
       // for the chunk it zeroed for (release)
-      if (threadIdx.x == 0) {
+      if (threadIdx.x == 0 && blk % lz.duty_every == 0) {
         const int c_duty = (int)(blk / lz.chunk_steps) + lz.lookahead;
         if (c_duty < lz.num_chunks) {
           __threadfence();
-          atomicAdd(lz.counters + c_duty, 1u);
+          red_add_u32(lz.counters + c_duty, 1u);
         }
       }
     }
@@ -673,7 +672,7 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
         // sticky word after the counters records it
         uint64_t t0 = 0;
         unsigned spins = 0;
-        while ((lz_seen = ld_acquire_gpu(lz_cnt)) < lz_need) {
+        while ((lz_seen = ld_relaxed_gpu(lz_cnt)) < lz_need) {
           if ((++spins & 1023u) == 0) {
             uint64_t now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -723,8 +722,8 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     e = e_n;
     active = active_n;
     if constexpr (LAZY) {
-      lz_d0 = lz_n0;
-      lz_d1 = lz_n1;
+      lz_b = lz_nb;
+      lz_e = lz_ne;
     }
 #pragma unroll
     for (int k = 0; k < N; ++k) rc[k] = nrc[k];
@@ -786,9 +785,12 @@ __global__ void __launch_bounds__(256)
 zero_ranges_kernel(T* __restrict__ y, const int2* __restrict__ ranges,
                    int num_ranges, unsigned* __restrict__ counters,
                    int num_counters, double* __restrict__ dot_xy) {
-  for (int r = blockIdx.x; r < num_ranges; r += gridDim.x) {
+  // one warp per piece (<= 128 dofs)
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < num_ranges; r += nwarps) {
     const int2 rg = __ldg(ranges + r);
-    for (int i = threadIdx.x; i < rg.y; i += blockDim.x) y[rg.x + i] = T(0);
+    for (int i = threadIdx.x & 31; i < rg.y; i += 32) y[rg.x + i] = T(0);
   }
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < num_counters; i += blockDim.x) counters[i] = 0u;
@@ -864,15 +866,18 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
     bool ok = op.lazy_epb == EPB &&
               cudaMallocAsync((void**)&counters, cbytes, stream) == cudaSuccess;
     if (ok) {
-      int zb = op.lazy_num_eager < 1 ? 1 : op.lazy_num_eager;
-      if (zb > num_sms() * 4) zb = num_sms() * 4;
+      int zb = (op.lazy_num_eager + 7) / 8;
+      if (zb < 1) zb = 1;
+      if (zb > num_sms() * 8) zb = num_sms() * 8;
       zero_ranges_kernel<T><<<zb, 256, 0, stream>>>(
-          (T*)y, op.lazy_eager, op.lazy_num_eager, counters,
+          (T*)y, op.lazy_pieces, op.lazy_num_eager, counters,
           op.lazy_num_chunks + 1, dot_xy);
       g_launch_count.fetch_add(1, std::memory_order_relaxed);
-      lz.duty = op.lazy_duty;
+      lz.pieces = op.lazy_pieces;
+      lz.duty_ptr = op.lazy_duty_ptr;
       lz.counters = counters;
       lz.chunk_steps = op.lazy_chunk_steps;
+      lz.duty_every = op.lazy_duty_every;
       lz.lookahead = op.lazy_lookahead;
       lz.num_chunks = op.lazy_num_chunks;
       cudaLaunchConfig_t cfg = {};

@@ -44,6 +44,19 @@ extern std::atomic<int64_t> g_launch_count;
     }                                                                         \
   } while (0)
 
+// Frees device allocations on every exit path of a set-up routine (the CUDA
+// check macros return early).
+struct DeviceFrees {
+  void* ptrs[8] = {};
+  int n = 0;
+  void add(void* p) {
+    if (p && n < 8) ptrs[n++] = p;
+  }
+  ~DeviceFrees() {
+    for (int i = 0; i < n; ++i) cudaFree(ptrs[i]);
+  }
+};
+
 // SM count of the CURRENT device (cached per device ordinal: a process may
 // drive several devices, and grids are sized from this).
 inline int num_sms() {
@@ -391,18 +404,34 @@ __device__ __forceinline__ bool scalar_allreduce_warp(const ScalarDev& sx,
 // written back.  Lazily, the CTA steps of element chunk c zero exactly the
 // dofs that chunk c + L touches FIRST, a few tens of MB of traffic ahead of
 // their first RED: the lines are still in L2 when the REDs arrive and go to
-// DRAM once.  `duty[step]` (host-built, sfem_op_set_lazy_zero) lists up to four
-// node ranges per CTA step; `counters[c]` counts the steps that finished their
-// share of chunk c; a step scatters only after counters[chunk of its last
-// element] reached the number of steps of chunk c - L (pipelined poll, a spin
-// only if a CTA runs more than L chunks ahead of the slowest one).
+// DRAM once (measured: DRAM traffic = 0.998 x the algorithmic bytes).
+//
+// Tables (host-built, sfem_op_set_lazy_zero): `pieces` = {start, len} node
+// ranges of at most 128 dofs; every `duty_every`-th CTA step ("duty step")
+// owns pieces [duty_ptr[q], duty_ptr[q+1]), q = step / duty_every, one piece
+// per thread.  `counters[c]` counts the duty steps that finished their share
+// of chunk c (ONE fence + RED per duty step: a fence per step cost 29 % of
+// the kernel, profiles/r02_ncu_apply3d_ne68_lazy_v1_fence_per_step.txt); a
+// step scatters only after counters[its chunk] reached the number of duty
+// steps of a chunk (poll issued one step early with a relaxed load: the REDs
+// that follow are L2 operations issued after the load returned and a block
+// barrier, so no acquire fence is needed on this side; a spin happens only if
+// a CTA runs more than L chunks ahead of the slowest one).
 struct LazyDev {
-  const int4* duty;     // (2 * num_steps): ranges {start0, len0, start1, len1} x 2
-  unsigned* counters;   // (num_chunks), zeroed before the launch
-  int chunk_steps;      // S: chunk of a CTA step = step / S
-  int lookahead;        // L
+  const int2* pieces;
+  const int32_t* duty_ptr;  // (num_duty + 1)
+  unsigned* counters;       // (num_chunks + 1), zeroed before the launch; the
+                            // last word is a sticky "a wait timed out" flag
+  int chunk_steps;          // S: chunk of a CTA step = step / S
+  int duty_every;           // Kd (divides S)
+  int lookahead;            // L
   int num_chunks;
 };
+
+__device__ __forceinline__ void red_add_u32(unsigned* addr, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v)
+               : "memory");
+}
 
 // symmetric index of (i,k), i<=k, in the packed d(d+1)/2 layout
 __host__ __device__ constexpr int sym_index(int dim, int i, int k) {
@@ -469,12 +498,12 @@ struct sfem_op {
   // accumulator were already zeroed by the previous cg_step_kernel
   bool prezeroed = false;
   // lazy zero fill (sfem_op_set_lazy_zero): device tables owned by the caller
-  const int4* lazy_duty = nullptr;     // 2 x int4 per CTA step of `lazy_epb`
-  const int2* lazy_eager = nullptr;    // ranges zeroed before the launch
+  const int2* lazy_pieces = nullptr;      // [0, lazy_num_eager): before launch
+  const int32_t* lazy_duty_ptr = nullptr; // (num_duty + 1) piece offsets
   int lazy_num_eager = 0;
   int64_t lazy_num_steps = 0;
-  int lazy_epb = 0, lazy_chunk_steps = 0, lazy_lookahead = 0;
-  int lazy_num_chunks = 0;
+  int lazy_epb = 0, lazy_chunk_steps = 0, lazy_duty_every = 0;
+  int lazy_lookahead = 0, lazy_num_chunks = 0;
 };
 
 // Peer-memory all-reduce handle (sfem_halo.cu).
@@ -491,7 +520,7 @@ namespace sfem {
 // fallback): the caller must not enqueue a fill.
 inline bool lazy_zero_applicable(const sfem_op& op, int ncomp) {
   const sfem_space_desc& d = op.base.desc;
-  return op.lazy_duty != nullptr && ncomp == 1 && op.variant == 0 &&
+  return op.lazy_duty_ptr != nullptr && ncomp == 1 && op.variant == 0 &&
          d.collocated && d.dim == 3 && d.n1d <= 16 && op.fuse == nullptr &&
          !op.prezeroed;
 }

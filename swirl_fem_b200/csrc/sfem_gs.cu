@@ -314,8 +314,11 @@ int pack_connectivity(const sfem_space_desc& desc, int n,
   SFEM_REQUIRE(G < (int64_t)kConnIdMask, "num_nodes must be < 2^30 - 1");
   int32_t* counts = nullptr;
   unsigned long long* d_nz = nullptr;
+  DeviceFrees guard;  // released on every return below
   SFEM_CUDA_CHECK(cudaMalloc(&counts, sizeof(int32_t) * (size_t)(G + 1)));
+  guard.add(counts);
   SFEM_CUDA_CHECK(cudaMalloc(&d_nz, sizeof(unsigned long long)));
+  guard.add(d_nz);
   SFEM_CUDA_CHECK(
       cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(G + 1), stream));
   SFEM_CUDA_CHECK(cudaMemsetAsync(d_nz, 0, sizeof(unsigned long long), stream));
@@ -336,8 +339,6 @@ int pack_connectivity(const sfem_space_desc& desc, int n,
                                   cudaMemcpyDeviceToHost, stream));
   SFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
   *n_zero = (int64_t)h_nz;
-  cudaFree(counts);
-  cudaFree(d_nz);
   return SFEM_OK;
 }
 
@@ -463,11 +464,19 @@ int sfem_scatter_plan_create(const int32_t* indices, int64_t count,
     *plan = p;
     return SFEM_OK;
   }
+  // the plan itself is released on every early (error) return
+  struct PlanGuard {
+    sfem_scatter_plan* p;
+    ~PlanGuard() { sfem_scatter_plan_destroy(p); }
+  } plan_guard{p};
+  DeviceFrees guard;  // temporaries
   int32_t *keys_in = nullptr, *vals_in = nullptr;
   void* tmp = nullptr;
   size_t tmp_bytes = 0;
   SFEM_CUDA_CHECK(cudaMalloc(&keys_in, sizeof(int32_t) * count));
+  guard.add(keys_in);
   SFEM_CUDA_CHECK(cudaMalloc(&vals_in, sizeof(int32_t) * count));
+  guard.add(vals_in);
   SFEM_CUDA_CHECK(cudaMalloc(&p->keys, sizeof(int32_t) * count));
   SFEM_CUDA_CHECK(cudaMalloc(&p->perm, sizeof(int32_t) * count));
   remap_sentinel_kernel<<<blocks_for(count), kThreads, 0, stream>>>(
@@ -481,6 +490,7 @@ int sfem_scatter_plan_create(const int32_t* indices, int64_t count,
       nullptr, tmp_bytes, keys_in, p->keys, vals_in, p->perm, (int)count, 0,
       end_bit, stream));
   SFEM_CUDA_CHECK(cudaMalloc(&tmp, tmp_bytes));
+  guard.add(tmp);
   // LSD radix sort is stable: equal keys keep ascending slot order.
   SFEM_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(
       tmp, tmp_bytes, keys_in, p->keys, vals_in, p->perm, (int)count, 0,
@@ -504,9 +514,7 @@ int sfem_scatter_plan_create(const int32_t* indices, int64_t count,
       lo = mid + 1;
   }
   p->nvalid = lo;
-  cudaFree(keys_in);
-  cudaFree(vals_in);
-  cudaFree(tmp);
+  plan_guard.p = nullptr;  // success: ownership passes to the caller
   *plan = p;
   return SFEM_OK;
 }

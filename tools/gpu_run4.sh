@@ -6,13 +6,12 @@ mkdir -p gpurun_out
 O=gpurun_out
 timeout 600 python -m pytest tests -m gpu -q -p no:cacheprovider --tb=short -k "lazy" > $O/r2_run4_pytest_lazy.log 2>&1
 tail -3 $O/r2_run4_pytest_lazy.log
-timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider --tb=short > $O/r2_run4_pytest.log 2>&1
-tail -3 $O/r2_run4_pytest.log
 B="python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline --no-extra --no-parity --cg-iters 30"
 SFEM_LAZY_ZERO=0 timeout 600 $B > $O/r2_lazy_off.json 2> $O/r2_lazy_off.err
-for cfg in "512 2" "256 2" "1024 2" "512 1" "1024 1" "2048 1" "512 3"; do
+rm -f $O/r2_lazy_c*.json
+for cfg in "512 2 8" "512 2 4" "512 2 16" "1024 2 8" "512 1 8" "1024 1 16" "2048 1 32" "256 3 8"; do
   set -- $cfg
-  SFEM_LAZY_CHUNK=$1 SFEM_LAZY_AHEAD=$2 timeout 600 $B > $O/r2_lazy_c$1_a$2.json 2> $O/r2_lazy_c$1_a$2.err
+  SFEM_LAZY_CHUNK=$1 SFEM_LAZY_AHEAD=$2 SFEM_LAZY_DUTY=$3 timeout 600 $B > $O/r2_lazy_c$1_a$2_d$3.json 2> $O/r2_lazy_c$1_a$2_d$3.err
 done
 for f in $O/r2_lazy_*.json; do python - "$f" <<'PY'
 import json,sys
