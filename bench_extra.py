@@ -268,16 +268,20 @@ def config3(device, timer):
 
 
 def sweep(device, timer, peak):
-  """C5 subset: order 4 and 8, 2-D (4.0 M dofs) and 3-D (8.1 M dofs), fp32 and
-  fp64, Laplacian apply."""
+  """C5 subset: order 4 and 8, 2-D (4.0 M dofs as SURVEY section 8d, and 16 M
+  dofs where the fixed costs of a launch no longer show) and 3-D (8.1 M dofs),
+  fp32 and fp64, Laplacian apply."""
   out = {}
-  for ndim, p, ne in ((2, 4, 500), (2, 8, 250), (3, 4, 50), (3, 8, 25)):
+  for ndim, p, ne, tag in ((2, 4, 500, ''), (2, 8, 250, ''),
+                           (2, 4, 1000, '_16M'), (2, 8, 500, '_16M'),
+                           (3, 4, 50, ''), (3, 8, 25, '')):
     refined, coords, bmask = _refined(ndim, ne, p + 1)
     for dt in ('f64', 'f32'):
       r = _apply_case(timer, refined, coords, bmask, ndim, p + 1, dt, device,
                       peak, lam=0.0, mu=1.0, with_mass=False)
-      out[f'{ndim}d_p{p}_{dt}'] = {k: r[k] for k in (
+      out[f'{ndim}d_p{p}_{dt}{tag}'] = {k: r[k] for k in (
           'dofs', 'apply_ms', 'gdof_per_s', 'algorithmic_bytes', 'frac')}
+    del refined, coords, bmask
   return out
 
 

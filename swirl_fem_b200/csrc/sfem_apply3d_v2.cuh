@@ -388,11 +388,22 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
   // LAZY: piece range of this step's zero duty (loaded one step ahead; empty
   // unless this is a duty step)
   int lz_b = 0, lz_e = 0;
+  // step-in-chunk / chunk / duty phase / duty index of the CURRENT step, kept
+  // incrementally (a 64-bit division per step and thread cost 1.8 us of a
+  // 4 us step: profiles/r02_ncu_apply3d_ne68_lazy_v2_int64_divisions.txt)
+  int lz_r = 0, lz_c = 0, lz_ph = 0, lz_q = 0;
+  int lz_gq = 0, lz_gph = 0;  // gridDim.x = lz_gq * duty_every + lz_gph
   if constexpr (LAZY) {
-    if (blk < nblocks && blk % lz.duty_every == 0) {
-      const int64_t q = blk / lz.duty_every;
-      lz_b = __ldg(lz.duty_ptr + q);
-      lz_e = __ldg(lz.duty_ptr + q + 1);
+    const int b0 = (int)blockIdx.x, g = (int)gridDim.x;
+    lz_c = b0 / lz.chunk_steps;
+    lz_r = b0 - lz_c * lz.chunk_steps;
+    lz_q = b0 / lz.duty_every;
+    lz_ph = b0 - lz_q * lz.duty_every;
+    lz_gq = g / lz.duty_every;
+    lz_gph = g - lz_gq * lz.duty_every;
+    if (blk < nblocks && lz_ph == 0) {
+      lz_b = __ldg(lz.duty_ptr + lz_q);
+      lz_e = __ldg(lz.duty_ptr + lz_q + 1);
     }
   }
 
@@ -406,18 +417,24 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     unsigned lz_seen = 0, lz_need = 0;
     const unsigned* lz_cnt = nullptr;
     int lz_nb = 0, lz_ne = 0;
+    int lz_nq = 0, lz_nph = 0;
     if constexpr (LAZY) {
       // chunk c's first-touch dofs are zeroed by the duty steps of chunk c - L
-      const int c_need = (int)(blk / lz.chunk_steps);
-      if (threadIdx.x == 0 && c_need >= lz.lookahead) {
-        lz_need = (unsigned)(lz.chunk_steps / lz.duty_every);
-        lz_cnt = lz.counters + c_need;
+      if (threadIdx.x == 0 && lz_c >= lz.lookahead) {
+        lz_need = (unsigned)lz.duty_per_chunk;
+        lz_cnt = lz.counters + lz_c;
         lz_seen = ld_relaxed_gpu(lz_cnt);
       }
-      if (blk_n < nblocks && blk_n % lz.duty_every == 0) {
-        const int64_t q = blk_n / lz.duty_every;
-        lz_nb = __ldg(lz.duty_ptr + q);
-        lz_ne = __ldg(lz.duty_ptr + q + 1);
+      // duty phase / index of the next step
+      lz_nq = lz_q + lz_gq;
+      lz_nph = lz_ph + lz_gph;
+      if (lz_nph >= lz.duty_every) {
+        lz_nph -= lz.duty_every;
+        ++lz_nq;
+      }
+      if (blk_n < nblocks && lz_nph == 0) {
+        lz_nb = __ldg(lz.duty_ptr + lz_nq);
+        lz_ne = __ldg(lz.duty_ptr + lz_nq + 1);
       }
     }
     const int64_t e_n = blk_n * epb + slot;
@@ -484,11 +501,14 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     __syncthreads();
 
     if constexpr (LAZY) {
-      // duty step: zero this step's pieces (one piece of <= 128 dofs per
-      // thread) of the dofs that chunk (c + L) touches first
-      for (int r = lz_b + (int)threadIdx.x; r < lz_e; r += (int)blockDim.x) {
+      // duty step: zero this step's pieces (<= 128 consecutive dofs each, one
+      // warp per piece: coalesced stores) of the dofs that chunk (c + L)
+      // touches first
+      for (int r = lz_b + (int)(threadIdx.x >> 5); r < lz_e;
+           r += (int)(blockDim.x >> 5)) {
         const int2 pc = __ldg(lz.pieces + r);
-        for (int i = 0; i < pc.y; ++i) y[pc.x + i] = T(0);
+        for (int i = (int)(threadIdx.x & 31); i < pc.y; i += 32)
+          y[pc.x + i] = T(0);
       }
     }
 
@@ -545,8 +565,8 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     if constexpr (LAZY) {
       // every thread's zero stores precede the barrier above: count this step
       // for the chunk it zeroed for (release)
-      if (threadIdx.x == 0 && blk % lz.duty_every == 0) {
-        const int c_duty = (int)(blk / lz.chunk_steps) + lz.lookahead;
+      if (threadIdx.x == 0 && lz_ph == 0) {
+        const int c_duty = lz_c + lz.lookahead;
         if (c_duty < lz.num_chunks) {
           __threadfence();
           red_add_u32(lz.counters + c_duty, 1u);
@@ -724,6 +744,13 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     if constexpr (LAZY) {
       lz_b = lz_nb;
       lz_e = lz_ne;
+      lz_q = lz_nq;
+      lz_ph = lz_nph;
+      lz_r += (int)gridDim.x;
+      while (lz_r >= lz.chunk_steps) {
+        lz_r -= lz.chunk_steps;
+        ++lz_c;
+      }
     }
 #pragma unroll
     for (int k = 0; k < N; ++k) rc[k] = nrc[k];
@@ -878,6 +905,7 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
       lz.counters = counters;
       lz.chunk_steps = op.lazy_chunk_steps;
       lz.duty_every = op.lazy_duty_every;
+      lz.duty_per_chunk = op.lazy_chunk_steps / op.lazy_duty_every;
       lz.lookahead = op.lazy_lookahead;
       lz.num_chunks = op.lazy_num_chunks;
       cudaLaunchConfig_t cfg = {};

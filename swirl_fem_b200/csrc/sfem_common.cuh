@@ -424,6 +424,7 @@ struct LazyDev {
                             // last word is a sticky "a wait timed out" flag
   int chunk_steps;          // S: chunk of a CTA step = step / S
   int duty_every;           // Kd (divides S)
+  int duty_per_chunk;       // S / Kd
   int lookahead;            // L
   int num_chunks;
 };

@@ -9,7 +9,7 @@ tail -3 $O/r2_run4_pytest_lazy.log
 B="python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline --no-extra --no-parity --cg-iters 30"
 SFEM_LAZY_ZERO=0 timeout 600 $B > $O/r2_lazy_off.json 2> $O/r2_lazy_off.err
 rm -f $O/r2_lazy_c*.json
-for cfg in "512 2 8" "512 2 4" "512 2 16" "1024 2 8" "512 1 8" "1024 1 16" "2048 1 32" "256 3 8"; do
+for cfg in "512 2 8" "1024 2 8" "512 4 8" "2048 2 16"; do
   set -- $cfg
   SFEM_LAZY_CHUNK=$1 SFEM_LAZY_AHEAD=$2 SFEM_LAZY_DUTY=$3 timeout 600 $B > $O/r2_lazy_c$1_a$2_d$3.json 2> $O/r2_lazy_c$1_a$2_d$3.err
 done
@@ -29,13 +29,6 @@ if [ -f $O/prof_lazy.ncu-rep ]; then
   python tools/ncu_summary.py $O/prof_lazy_raw.csv > $O/r2_ncu_apply3d_ne68_lazy.txt
   ncu -i $O/prof_lazy.ncu-rep --page source --csv 2>/dev/null | gzip > $O/r2_source_apply3d_ne68_lazy.csv.gz
   rm -f $O/prof_lazy_raw.csv $O/prof_lazy.ncu-rep
-fi
-SFEM_LAZY_ZERO=0 timeout 900 ncu --set full --clock-control none -k regex:apply3d_v2 -s 8 -c 1 -o $O/prof_eager -f \
-  python bench.py --steps 4 --warmup 5 --no-e2e --no-cpu-baseline --no-extra --no-parity --cg-iters 0 > $O/r2_ncu_eager.log 2>&1
-if [ -f $O/prof_eager.ncu-rep ]; then
-  ncu -i $O/prof_eager.ncu-rep --page raw --csv > $O/prof_eager_raw.csv 2>/dev/null
-  python tools/ncu_summary.py $O/prof_eager_raw.csv > $O/r2_ncu_apply3d_ne68_eager.txt
-  rm -f $O/prof_eager_raw.csv $O/prof_eager.ncu-rep
 fi
 du -sh $O
 echo done
