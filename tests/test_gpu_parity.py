@@ -481,6 +481,54 @@ def test_lazy_zero_fill_matches_oracle(case):
       1e-14 if dtype == torch.float64 else 1e-6)
 
 
+def test_host_pipeline_matches_resident_apply():
+  """`HostPipeline` (upload / apply / download overlapped on three streams,
+  double-buffered): every submitted host vector gets ITS result, in order,
+  equal to the device-resident apply of the same vector."""
+  from swirl_fem_b200.core.operator import HostPipeline
+  refined, mesh, space, oracle, bmask = _build(3, 4, 5, GLL, 5, torch.float64)
+  op = space.operator(dirichlet_mask=bmask, with_mass=True)
+  rng = np.random.default_rng(3)
+  xs = [torch.as_tensor(rng.standard_normal(mesh.num_nodes)).pin_memory()
+        for _ in range(5)]
+  ys = [torch.empty(mesh.num_nodes, dtype=torch.float64).pin_memory()
+        for _ in range(5)]
+  pipe = HostPipeline(op, depth=2)
+  for x, y in zip(xs, ys):
+    pipe.submit(x, y, lam=0.5, mu=1.0)
+  pipe.synchronize()
+  interior = 1.0 - bmask
+  for x, y in zip(xs, ys):
+    want = oracle.apply(x.numpy(), lam=0.5, mu=1.0, interior_mask=interior)
+    assert rel_err(y, want) < 1e-12
+  with pytest.raises(ValueError, match='pinned'):
+    pipe.submit(torch.zeros(mesh.num_nodes, dtype=torch.float64), ys[0])
+
+
+def test_vector_gather_scatter_exchange_one_launch():
+  """`offset = -1` mode of sfem_gather / sfem_scatter_add / sfem_exchange (all
+  components of an AoS field in one launch) equals the per-component calls,
+  bit for bit (gather, exchange) / to rounding (atomic scatter)."""
+  from swirl_fem_b200 import _lib
+  refined = helpers.deformed_premesh(2, 4, 4, periodic_dims=(1,))
+  mesh = refined.finalize()
+  rng = np.random.default_rng(4)
+  u = dev(rng.standard_normal((mesh.num_nodes, 3)))
+  g_all = _lib.gather(u, mesh.elements, fill_value=0.)
+  g_one = torch.stack([mesh.gather(u[:, k].contiguous()) for k in range(3)], -1)
+  assert torch.equal(g_all, g_one)
+  ul = dev(rng.standard_normal(tuple(mesh.elements.shape) + (3,)))
+  s_all = _lib.scatter(ul, mesh.elements, mesh.num_nodes)
+  s_one = torch.stack([mesh.scatter(ul[..., k].contiguous())
+                       for k in range(3)], -1)
+  assert rel_err(s_all.cpu(), s_one.cpu().numpy()) < 1e-14
+  e_all = _lib.exchange(u, mesh.exchange_gather_indices,
+                        mesh.exchange_unique_indices)
+  e_one = torch.stack([mesh.exchange(u[:, k].contiguous())
+                       for k in range(3)], -1)
+  assert rel_err(e_all.cpu(), e_one.cpu().numpy()) < 1e-14
+
+
 def test_operator_properties_large():
   """Size-independent properties at a size the oracle cannot reach."""
   from swirl_fem_b200.core.fespace import FiniteElementSpace
