@@ -253,23 +253,26 @@ int sfem_op_set_variant(sfem_op* op, int32_t variant);
  * element chunk c zero the dofs that chunk c + lookahead touches FIRST, while
  * they are still L2-resident when the REDs arrive.
  *   sfem_op_step_elems: elements per CTA step.  A chunk is `chunk_steps`
- *     consecutive steps; every `duty_every`-th step (duty_every divides
- *     chunk_steps) is a duty step.
- *   pieces (device int2[]): {start, len <= 128} node ranges.  The first
- *     `num_eager` are zeroed before the launch (dofs first touched by chunks
- *     < lookahead, or by no element); duty step q = step / duty_every owns
- *     pieces [duty_ptr[q], duty_ptr[q + 1]) (device int32[num_duty + 1]) and
- *     must belong to chunk(first touch of those dofs) - lookahead.  All pieces
- *     together cover [0, sfem_op_num_zero) exactly once.  Tables are retained
- *     (not copied); duty_ptr = NULL switches back to the eager fill. */
+ *     consecutive steps.
+ *   pieces (device int2[num_pieces]): {start, len | chunk << 8}, len <= 128,
+ *     sorted by the chunk that touches the dofs first; the first `num_eager`
+ *     (dofs of chunks < lookahead, or touched by no element) are zeroed before
+ *     the launch; chunk_ptr (device int32[num_chunks + 1]) = first piece of
+ *     every chunk.  All pieces together cover [0, sfem_op_num_zero) exactly
+ *     once.  Inside the kernel the pieces are a work queue: every
+ *     `duty_every`-th step of a CTA claims and zeroes `batch` pieces, at most
+ *     `max_ahead` chunks ahead of its own position.  Tables are retained (not
+ *     copied); chunk_ptr = NULL switches back to the eager fill.  At most 8
+ *     applies of one handle may be in flight at once in this mode. */
 int32_t sfem_op_step_elems(const sfem_op* op);
 /* Length of the prefix y[0 .. n) that holds every dof touched by more than one
  * element (or by none): what an apply zeroes before accumulating. */
 int64_t sfem_op_num_zero(const sfem_op* op);
-int sfem_op_set_lazy_zero(sfem_op* op, const void* pieces, int32_t num_eager,
-                          const int32_t* duty_ptr, int64_t num_duty,
-                          int32_t chunk_steps, int32_t duty_every,
-                          int32_t lookahead);
+int sfem_op_set_lazy_zero(sfem_op* op, const void* pieces, int32_t num_pieces,
+                          int32_t num_eager, const int32_t* chunk_ptr,
+                          int32_t num_chunks, int32_t chunk_steps,
+                          int32_t lookahead, int32_t max_ahead,
+                          int32_t duty_every, int32_t batch);
 
 /* ------------------------------------------------------------------------ */
 /* Peer-memory halo exchange (partitioned QQ^T over NVLink P2P stores)       */

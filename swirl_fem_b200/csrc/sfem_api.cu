@@ -179,6 +179,14 @@ int op_apply_internal(const sfem_op* op, double lambda, double mu,
 
 }  // namespace sfem
 
+static void lazy_release(sfem_op* op) {
+  op->lazy_chunk_ptr = nullptr;
+  if (op->lazy_counters) cudaFree(op->lazy_counters);
+  op->lazy_counters = nullptr;
+  delete op->lazy_seq;
+  op->lazy_seq = nullptr;
+}
+
 extern "C" {
 
 const char* sfem_last_error(void) { return sfem::g_last_error.c_str(); }
@@ -325,6 +333,7 @@ int sfem_op_create(const sfem_space_desc* desc, const uint8_t* dirichlet,
 
 void sfem_op_destroy(sfem_op* op) {
   if (!op) return;
+  lazy_release(op);
   sfem::space_base_free(&op->base);
   delete op;
 }
@@ -340,37 +349,44 @@ int32_t sfem_op_step_elems(const sfem_op* op) {
                              : step_elems_3d<float>(d.n1d, op->with_mass != 0);
 }
 
-int sfem_op_set_lazy_zero(sfem_op* op, const void* pieces, int32_t num_eager,
-                          const int32_t* duty_ptr, int64_t num_duty,
-                          int32_t chunk_steps, int32_t duty_every,
-                          int32_t lookahead) {
+int sfem_op_set_lazy_zero(sfem_op* op, const void* pieces, int32_t num_pieces,
+                          int32_t num_eager, const int32_t* chunk_ptr,
+                          int32_t num_chunks, int32_t chunk_steps,
+                          int32_t lookahead, int32_t max_ahead,
+                          int32_t duty_every, int32_t batch) {
   using namespace sfem;
   SFEM_REQUIRE(op, "null argument");
-  if (duty_ptr == nullptr) {  // switch off
-    op->lazy_duty_ptr = nullptr;
-    return SFEM_OK;
-  }
+  lazy_release(op);
+  if (chunk_ptr == nullptr) return SFEM_OK;  // switched off
   const int epb = sfem_op_step_elems(op);
   SFEM_REQUIRE(epb > 0, "lazy zero fill: 3-D collocated operators only");
   const int64_t E = op->base.desc.num_elements;
   const int64_t num_steps = (E + epb - 1) / epb;
-  SFEM_REQUIRE(pieces != nullptr && num_eager >= 0, "lazy zero fill: no pieces");
-  SFEM_REQUIRE(duty_every >= 1 && chunk_steps >= duty_every &&
-                   chunk_steps % duty_every == 0 && lookahead >= 1,
+  SFEM_REQUIRE(pieces != nullptr && num_pieces >= 0 && num_eager >= 0 &&
+                   num_eager <= num_pieces,
+               "lazy zero fill: bad piece table");
+  SFEM_REQUIRE(chunk_steps >= 1 && duty_every >= 1 && batch >= 1 &&
+                   lookahead >= 1 && max_ahead >= lookahead,
                "lazy zero fill: bad chunking");
-  SFEM_REQUIRE(num_duty == (num_steps + duty_every - 1) / duty_every,
-               "lazy zero fill: duty table does not match the step count");
-  SFEM_REQUIRE(op->base.desc.num_nodes < ((int64_t)1 << 31),
-               "lazy zero fill: node ids must fit 31 bits");
+  SFEM_REQUIRE(num_chunks == (num_steps + chunk_steps - 1) / chunk_steps,
+               "lazy zero fill: chunk table does not match the step count");
+  SFEM_REQUIRE(op->base.desc.num_nodes < ((int64_t)1 << 31) &&
+                   num_chunks < (1 << 23),
+               "lazy zero fill: ids / chunk ids out of range");
+  const size_t words = (size_t)8 * ((size_t)num_chunks + 2);
+  SFEM_CUDA_CHECK(cudaMalloc(&op->lazy_counters, words * sizeof(unsigned)));
+  op->lazy_seq = new std::atomic<unsigned>(0);
   op->lazy_pieces = (const int2*)pieces;
-  op->lazy_duty_ptr = duty_ptr;
+  op->lazy_chunk_ptr = chunk_ptr;
+  op->lazy_num_pieces = num_pieces;
   op->lazy_num_eager = num_eager;
-  op->lazy_num_steps = num_steps;
   op->lazy_epb = epb;
   op->lazy_chunk_steps = chunk_steps;
   op->lazy_duty_every = duty_every;
+  op->lazy_batch = batch;
   op->lazy_lookahead = lookahead;
-  op->lazy_num_chunks = (int)((num_steps + chunk_steps - 1) / chunk_steps);
+  op->lazy_max_ahead = max_ahead;
+  op->lazy_num_chunks = num_chunks;
   return SFEM_OK;
 }
 

@@ -385,26 +385,47 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       nrc_c[k] = a1 ? ld_stream(conn + e1 * n + k * P + t) : kConnSentinel;
   }
 
-  // LAZY: piece range of this step's zero duty (loaded one step ahead; empty
-  // unless this is a duty step)
-  int lz_b = 0, lz_e = 0;
-  // step-in-chunk / chunk / duty phase / duty index of the CURRENT step, kept
-  // incrementally (a 64-bit division per step and thread cost 1.8 us of a
-  // 4 us step: profiles/r02_ncu_apply3d_ne68_lazy_v2_int64_divisions.txt)
-  int lz_r = 0, lz_c = 0, lz_ph = 0, lz_q = 0;
-  int lz_gq = 0, lz_gph = 0;  // gridDim.x = lz_gq * duty_every + lz_gph
-  if constexpr (LAZY) {
-    const int b0 = (int)blockIdx.x, g = (int)gridDim.x;
-    lz_c = b0 / lz.chunk_steps;
-    lz_r = b0 - lz_c * lz.chunk_steps;
-    lz_q = b0 / lz.duty_every;
-    lz_ph = b0 - lz_q * lz.duty_every;
-    lz_gq = g / lz.duty_every;
-    lz_gph = g - lz_gq * lz.duty_every;
-    if (blk < nblocks && lz_ph == 0) {
-      lz_b = __ldg(lz.duty_ptr + lz_q);
-      lz_e = __ldg(lz.duty_ptr + lz_q + 1);
+  // LAZY (work queue, see LazyDev): chunk of the current step kept
+  // incrementally; this CTA's own step counter selects its duty steps
+  int lz_r = 0, lz_c = 0, lz_own = 0;
+  unsigned lz_base = 0xffffffffu;  // thread 0: claim issued at the last duty
+                                   // step (none yet)
+  unsigned lz_head = 0;            // thread 0: lower bound of the queue head
+  __shared__ unsigned s_lz[2];     // [0] claimed base, [1] "this step waits"
+  auto lz_zero_batch = [&](unsigned base) {
+    // pieces [base, base + batch): a warp takes groups of 8 consecutive pieces
+    // (descriptors loaded together, coalesced zero stores), fences ONCE after
+    // its last store, and only then counts its pieces on their chunks' counters
+    // (lane j counts the j-th piece of a group)
+    const unsigned end =
+        base + (unsigned)lz.batch < (unsigned)lz.num_pieces
+            ? base + (unsigned)lz.batch
+            : (unsigned)lz.num_pieces;
+    const unsigned w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = (int)(threadIdx.x & 31);
+    for (unsigned r0 = base + w * 8u; r0 < end; r0 += nw * 8u) {
+      int2 pcs[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        pcs[j] = r0 + j < end ? __ldg(lz.pieces + r0 + j) : make_int2(0, 0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int len = pcs[j].y & 0xff;
+        for (int i = lane; i < len; i += 32) y[pcs[j].x + i] = T(0);
+      }
     }
+    __threadfence();
+    __syncwarp();
+    for (unsigned r0 = base + w * 8u; r0 < end; r0 += nw * 8u) {
+      if (lane < 8 && r0 + lane < end) {
+        const int2 pc = __ldg(lz.pieces + r0 + lane);
+        red_add_u32(lz.counters + (pc.y >> 8), 1u);
+      }
+    }
+  };
+  if constexpr (LAZY) {
+    lz_c = (int)blockIdx.x / lz.chunk_steps;
+    lz_r = (int)blockIdx.x - lz_c * lz.chunk_steps;
   }
 
   int buf = 0;
@@ -413,28 +434,34 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     T* sUn = sU0 + (buf ^ 1) * C::tile;
     // ---- pipeline: next element's factors -> L2, connectivity -> registers
     const int64_t blk_n = blk + gridDim.x;
-    // LAZY: issue the counter poll now, look at it before the scatter
+    // LAZY: poll the counter of this step's chunk now, look at it before the
+    // scatter; on a duty step publish the claim issued one duty step ago and
+    // issue the next one (its result is not needed before the next duty step)
     unsigned lz_seen = 0, lz_need = 0;
-    const unsigned* lz_cnt = nullptr;
-    int lz_nb = 0, lz_ne = 0;
-    int lz_nq = 0, lz_nph = 0;
+    const bool lz_duty = LAZY && (lz_own % lz.duty_every) == 0;
     if constexpr (LAZY) {
-      // chunk c's first-touch dofs are zeroed by the duty steps of chunk c - L
-      if (threadIdx.x == 0 && lz_c >= lz.lookahead) {
-        lz_need = (unsigned)lz.duty_per_chunk;
-        lz_cnt = lz.counters + lz_c;
-        lz_seen = ld_relaxed_gpu(lz_cnt);
-      }
-      // duty phase / index of the next step
-      lz_nq = lz_q + lz_gq;
-      lz_nph = lz_ph + lz_gph;
-      if (lz_nph >= lz.duty_every) {
-        lz_nph -= lz.duty_every;
-        ++lz_nq;
-      }
-      if (blk_n < nblocks && lz_nph == 0) {
-        lz_nb = __ldg(lz.duty_ptr + lz_nq);
-        lz_ne = __ldg(lz.duty_ptr + lz_nq + 1);
+      if (threadIdx.x == 0) {
+        if (lz_c >= lz.lookahead) {
+          lz_need = (unsigned)(__ldg(lz.chunk_ptr + lz_c + 1) -
+                               __ldg(lz.chunk_ptr + lz_c));
+          lz_seen = ld_relaxed_gpu(lz.counters + lz_c);
+        }
+        if (lz_duty) {
+          s_lz[0] = lz_base;  // visible after the barrier below
+          // keep the queue at most `max_ahead` chunks ahead of this CTA (the
+          // last returned base is a lower bound of the queue head)
+          const int c_lim = lz_c + lz.max_ahead < lz.num_chunks
+                                ? lz_c + lz.max_ahead
+                                : lz.num_chunks;
+          const unsigned limit = (unsigned)__ldg(lz.chunk_ptr + c_lim);
+          const bool below = lz_head < limit;
+          lz_base = 0xffffffffu;
+          if (below) {
+            lz_base = atomicAdd(lz.counters + lz.num_chunks + 1,
+                                (unsigned)lz.batch);
+            lz_head = lz_base;  // (used only after it has arrived)
+          }
+        }
       }
     }
     const int64_t e_n = blk_n * epb + slot;
@@ -501,14 +528,10 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     __syncthreads();
 
     if constexpr (LAZY) {
-      // duty step: zero this step's pieces (<= 128 consecutive dofs each, one
-      // warp per piece: coalesced stores) of the dofs that chunk (c + L)
-      // touches first
-      for (int r = lz_b + (int)(threadIdx.x >> 5); r < lz_e;
-           r += (int)(blockDim.x >> 5)) {
-        const int2 pc = __ldg(lz.pieces + r);
-        for (int i = (int)(threadIdx.x & 31); i < pc.y; i += 32)
-          y[pc.x + i] = T(0);
+      // duty step: zero the batch claimed one duty step ago
+      if (lz_duty) {
+        const unsigned base = s_lz[0];
+        if (base < (unsigned)lz.num_pieces) lz_zero_batch(base);
       }
     }
 
@@ -561,18 +584,6 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       for (int j = 0; j < N; ++j) sB[baseC + (SWZ ? (j ^ qs) : j)] = out[j];
     }
     __syncthreads();
-
-    if constexpr (LAZY) {
-      // every thread's zero stores precede the barrier above: count this step
-      // for the chunk it zeroed for (release)
-      if (threadIdx.x == 0 && lz_ph == 0) {
-        const int c_duty = lz_c + lz.lookahead;
-        if (c_duty < lz.num_chunks) {
-          __threadfence();
-          red_add_u32(lz.counters + c_duty, 1u);
-        }
-      }
-    }
 
     if (HALO) {
       if (hstate == kHFenced && hticket == 0) {
@@ -685,27 +696,55 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       for (int j = 0; j < N; ++j) sB[baseC + (SWZ ? (j ^ qs) : j)] = out[j];
     }
     if constexpr (LAZY) {
-      // the dofs this step scatters into have been zeroed once every step of
-      // chunk (c - L) has counted itself (normally long ago: no spin)
-      if (threadIdx.x == 0 && lz_cnt != nullptr && lz_seen < lz_need) {
-        // bounded (~2 s): inconsistent tables must not hang the device; the
-        // sticky word after the counters records it
-        uint64_t t0 = 0;
-        unsigned spins = 0;
-        while ((lz_seen = ld_relaxed_gpu(lz_cnt)) < lz_need) {
-          if ((++spins & 1023u) == 0) {
-            uint64_t now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (t0 == 0) t0 = now;
-            if (now - t0 > 2000000000ull) {
-              atomicExch(lz.counters + lz.num_chunks, 1u);
-              break;
-            }
-          }
-        }
+      // the dofs this step scatters into are zero once every piece of its
+      // chunk has been counted (normally long ago)
+      if (threadIdx.x == 0) {
+        if (lz_seen < lz_need) lz_seen = ld_relaxed_gpu(lz.counters + lz_c);
+        s_lz[1] = lz_seen < lz_need;
       }
     }
     __syncthreads();
+    if constexpr (LAZY) {
+      // not yet: HELP -- claim and zero batches until the chunk is complete (a
+      // CTA that only waited could wait for pieces nobody has claimed yet);
+      // bounded (~2 s): inconsistent tables must not hang the device
+      if (s_lz[1]) {
+        uint64_t t0 = 0;
+        for (unsigned spins = 0;; ++spins) {
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            // first the batch this CTA still holds from its last duty step (a
+            // waiting CTA must not sit on claimed pieces), then new ones
+            if (lz_base != 0xffffffffu) {
+              s_lz[0] = lz_base;
+              lz_base = 0xffffffffu;
+            } else {
+              s_lz[0] = atomicAdd(lz.counters + lz.num_chunks + 1,
+                                  (unsigned)lz.batch);
+            }
+          }
+          __syncthreads();
+          const unsigned base = s_lz[0];
+          if (base < (unsigned)lz.num_pieces) lz_zero_batch(base);
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            bool done = ld_relaxed_gpu(lz.counters + lz_c) >= lz_need;
+            if (!done && (spins & 63u) == 63u) {
+              uint64_t now;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+              if (t0 == 0) t0 = now;
+              if (now - t0 > 2000000000ull) {
+                atomicExch(lz.counters + lz.num_chunks, 1u);
+                done = true;
+              }
+            }
+            s_lz[1] = !done;
+          }
+          __syncthreads();
+          if (!s_lz[1]) break;
+        }
+      }
+    }
 
     // ---- phase 5 (mapping A): sum the three parts, scatter
     if (first_step) {
@@ -742,10 +781,7 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     e = e_n;
     active = active_n;
     if constexpr (LAZY) {
-      lz_b = lz_nb;
-      lz_e = lz_ne;
-      lz_q = lz_nq;
-      lz_ph = lz_nph;
+      ++lz_own;
       lz_r += (int)gridDim.x;
       while (lz_r >= lz.chunk_steps) {
         lz_r -= lz.chunk_steps;
@@ -811,17 +847,23 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 zero_ranges_kernel(T* __restrict__ y, const int2* __restrict__ ranges,
                    int num_ranges, unsigned* __restrict__ counters,
-                   int num_counters, double* __restrict__ dot_xy) {
-  // one warp per piece (<= 128 dofs)
+                   int num_chunks, double* __restrict__ dot_xy) {
+  // one warp per piece (<= 128 dofs; the chunk id sits above bit 8 of .y)
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int r = warp; r < num_ranges; r += nwarps) {
     const int2 rg = __ldg(ranges + r);
-    for (int i = threadIdx.x & 31; i < rg.y; i += 32) y[rg.x + i] = T(0);
+    const int len = rg.y & 0xff;
+    for (int i = threadIdx.x & 31; i < len; i += 32) y[rg.x + i] = T(0);
   }
   if (blockIdx.x == 0) {
-    for (int i = threadIdx.x; i < num_counters; i += blockDim.x) counters[i] = 0u;
-    if (threadIdx.x == 0 && dot_xy) *dot_xy = 0.0;
+    // chunk counters and the timeout flag to 0, the queue head to the first
+    // piece that is not zeroed here
+    for (int i = threadIdx.x; i <= num_chunks; i += blockDim.x) counters[i] = 0u;
+    if (threadIdx.x == 0) {
+      counters[num_chunks + 1] = (unsigned)num_ranges;
+      if (dot_xy) *dot_xy = 0.0;
+    }
   }
 }
 
@@ -887,27 +929,33 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
     // chunk counters need every CTA resident); any failure falls back to the
     // eager fill + the ordinary kernel
     static_assert(!HALO && !LOCAL, "lazy zero fill: plain global apply only");
-    // + 1: sticky "a wait timed out" word
-    const size_t cbytes = sizeof(unsigned) * ((size_t)op.lazy_num_chunks + 1);
+    // one of the handle's 8 counter blocks (launches of one handle may overlap
+    // on different streams: up to 8 in flight)
     unsigned* counters = nullptr;
-    bool ok = op.lazy_epb == EPB &&
-              cudaMallocAsync((void**)&counters, cbytes, stream) == cudaSuccess;
+    const bool ok = op.lazy_epb == EPB && op.lazy_counters && op.lazy_seq;
     if (ok) {
+      const unsigned slot = op.lazy_seq->fetch_add(1u) & 7u;
+      counters = op.lazy_counters + (size_t)slot * ((size_t)op.lazy_num_chunks + 2);
       int zb = (op.lazy_num_eager + 7) / 8;
       if (zb < 1) zb = 1;
       if (zb > num_sms() * 8) zb = num_sms() * 8;
       zero_ranges_kernel<T><<<zb, 256, 0, stream>>>(
           (T*)y, op.lazy_pieces, op.lazy_num_eager, counters,
-          op.lazy_num_chunks + 1, dot_xy);
+          op.lazy_num_chunks, dot_xy);
       g_launch_count.fetch_add(1, std::memory_order_relaxed);
       lz.pieces = op.lazy_pieces;
-      lz.duty_ptr = op.lazy_duty_ptr;
+      lz.chunk_ptr = op.lazy_chunk_ptr;
       lz.counters = counters;
       lz.chunk_steps = op.lazy_chunk_steps;
       lz.duty_every = op.lazy_duty_every;
-      lz.duty_per_chunk = op.lazy_chunk_steps / op.lazy_duty_every;
+      // a warp zeroes groups of 8 pieces: keep a batch within a few groups
+      lz.batch = op.lazy_batch < 32 * (C::threads / 32)
+                     ? op.lazy_batch
+                     : 32 * (C::threads / 32);
       lz.lookahead = op.lazy_lookahead;
+      lz.max_ahead = op.lazy_max_ahead;
       lz.num_chunks = op.lazy_num_chunks;
+      lz.num_pieces = op.lazy_num_pieces;
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = grid;
       cfg.blockDim = dim3(C::threads);
@@ -921,7 +969,6 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
       const cudaError_t e = cudaLaunchKernelEx(
           &cfg, kernel, dm, (const uint32_t*)op.conn, (const T*)op.geom,
           (T)lambda, (T)mu, (const T*)x, (T*)y, ncomp, E, dot_xy, hd, lz);
-      cudaFreeAsync(counters, stream);
       if (e == cudaSuccess) {
         SFEM_LAUNCH_CHECK();
         return SFEM_OK;

@@ -406,27 +406,36 @@ __device__ __forceinline__ bool scalar_allreduce_warp(const ScalarDev& sx,
 // their first RED: the lines are still in L2 when the REDs arrive and go to
 // DRAM once (measured: DRAM traffic = 0.998 x the algorithmic bytes).
 //
-// Tables (host-built, sfem_op_set_lazy_zero): `pieces` = {start, len} node
-// ranges of at most 128 dofs; every `duty_every`-th CTA step ("duty step")
-// owns pieces [duty_ptr[q], duty_ptr[q+1]), q = step / duty_every, one piece
-// per thread.  `counters[c]` counts the duty steps that finished their share
-// of chunk c (ONE fence + RED per duty step: a fence per step cost 29 % of
-// the kernel, profiles/r02_ncu_apply3d_ne68_lazy_v1_fence_per_step.txt); a
-// step scatters only after counters[its chunk] reached the number of duty
-// steps of a chunk (poll issued one step early with a relaxed load: the REDs
-// that follow are L2 operations issued after the load returned and a block
-// barrier, so no acquire fence is needed on this side; a spin happens only if
-// a CTA runs more than L chunks ahead of the slowest one).
+// Tables (host-built, sfem_op_set_lazy_zero): `pieces` = {start, len | chunk
+// << 8} node ranges of at most 128 dofs, sorted by the chunk that touches them
+// first; `chunk_ptr[c]` = first piece of chunk c.  The kernel treats them as a
+// WORK QUEUE: every `duty_every`-th step of a CTA claims `batch` pieces
+// (atomicAdd on the queue head, issued one duty step early so that its latency
+// is never waited for), zeroes them (one warp per piece, every writer fences,
+// lane 0 counts the piece on its chunk's counter) -- so the zeroing is done by
+// whichever CTAs run, in first-touch order, a few chunks ahead of the fastest
+// CTA, and a slow CTA never holds anyone up.  (Statically assigned duties --
+// chunk c zeroed by the steps of chunk c - L -- coupled every CTA to the
+// slowest one: 24-45 % slower than the eager fill,
+// profiles/r02_lazy_zero_v3_static_duty_bench.txt.)  A step scatters only
+// after counters[its chunk] == number of pieces of the chunk (relaxed poll
+// issued a step early; the REDs that follow are L2 operations issued after the
+// load returned and a block barrier, so this side needs no acquire fence); a
+// CTA that finds its chunk incomplete HELPS (claims and zeroes batches) until
+// it is, so waiting can never deadlock.
 struct LazyDev {
   const int2* pieces;
-  const int32_t* duty_ptr;  // (num_duty + 1)
-  unsigned* counters;       // (num_chunks + 1), zeroed before the launch; the
-                            // last word is a sticky "a wait timed out" flag
-  int chunk_steps;          // S: chunk of a CTA step = step / S
-  int duty_every;           // Kd (divides S)
-  int duty_per_chunk;       // S / Kd
-  int lookahead;            // L
+  const int32_t* chunk_ptr;  // (num_chunks + 1)
+  unsigned* counters;        // [0, num_chunks): pieces done per chunk;
+                             // [num_chunks]: sticky "a wait timed out";
+                             // [num_chunks + 1]: queue head (next piece)
+  int chunk_steps;           // S: chunk of a CTA step = step / S
+  int duty_every;            // a CTA claims a batch every k-th of ITS steps
+  int batch;                 // pieces per claim
+  int lookahead;             // chunks < lookahead are zeroed before the launch
+  int max_ahead;             // the queue stays <= this many chunks ahead
   int num_chunks;
+  int num_pieces;
 };
 
 __device__ __forceinline__ void red_add_u32(unsigned* addr, unsigned v) {
@@ -499,12 +508,15 @@ struct sfem_op {
   // accumulator were already zeroed by the previous cg_step_kernel
   bool prezeroed = false;
   // lazy zero fill (sfem_op_set_lazy_zero): device tables owned by the caller
-  const int2* lazy_pieces = nullptr;      // [0, lazy_num_eager): before launch
-  const int32_t* lazy_duty_ptr = nullptr; // (num_duty + 1) piece offsets
-  int lazy_num_eager = 0;
-  int64_t lazy_num_steps = 0;
-  int lazy_epb = 0, lazy_chunk_steps = 0, lazy_duty_every = 0;
-  int lazy_lookahead = 0, lazy_num_chunks = 0;
+  const int2* lazy_pieces = nullptr;       // [0, lazy_num_eager): before launch
+  const int32_t* lazy_chunk_ptr = nullptr; // (num_chunks + 1) piece offsets
+  int lazy_num_eager = 0, lazy_num_pieces = 0;
+  int lazy_epb = 0, lazy_chunk_steps = 0, lazy_duty_every = 0, lazy_batch = 0;
+  int lazy_lookahead = 0, lazy_max_ahead = 0, lazy_num_chunks = 0;
+  // library-owned: ring of 8 counter blocks (one per launch in flight) and the
+  // launch sequence number that picks the block
+  unsigned* lazy_counters = nullptr;
+  std::atomic<unsigned>* lazy_seq = nullptr;
 };
 
 // Peer-memory all-reduce handle (sfem_halo.cu).
@@ -521,7 +533,7 @@ namespace sfem {
 // fallback): the caller must not enqueue a fill.
 inline bool lazy_zero_applicable(const sfem_op& op, int ncomp) {
   const sfem_space_desc& d = op.base.desc;
-  return op.lazy_duty_ptr != nullptr && ncomp == 1 && op.variant == 0 &&
+  return op.lazy_chunk_ptr != nullptr && ncomp == 1 && op.variant == 0 &&
          d.collocated && d.dim == 3 && d.n1d <= 16 && op.fuse == nullptr &&
          !op.prezeroed;
 }

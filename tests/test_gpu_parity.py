@@ -451,7 +451,8 @@ def test_lazy_zero_fill_matches_oracle(case):
   eager = {}
   for lam, mu in ((0.0, 1.0), (0.7, 1.3)):
     eager[(lam, mu)] = op.apply(ud, lam=lam, mu=mu)
-  assert op.enable_lazy_zero(chunk_elems=64, lookahead=2, duty_every=4)
+  assert op.enable_lazy_zero(chunk_elems=64, lookahead=2, max_ahead=3,
+                             duty_every=4)
   tol = TOL[dtype]
   for lam, mu in ((0.0, 1.0), (0.7, 1.3)):
     want = oracle.apply(u, lam=lam, mu=mu, interior_mask=interior)

@@ -9,9 +9,9 @@ tail -3 $O/r2_run4_pytest_lazy.log
 B="python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline --no-extra --no-parity --cg-iters 30"
 SFEM_LAZY_ZERO=0 timeout 600 $B > $O/r2_lazy_off.json 2> $O/r2_lazy_off.err
 rm -f $O/r2_lazy_c*.json
-for cfg in "512 2 8" "1024 2 8" "512 4 8" "2048 2 16"; do
+for cfg in "512 2 4 32" "512 2 4 8" "512 2 8 32" "1024 2 4 64" "256 2 6 16"; do
   set -- $cfg
-  SFEM_LAZY_CHUNK=$1 SFEM_LAZY_AHEAD=$2 SFEM_LAZY_DUTY=$3 timeout 600 $B > $O/r2_lazy_c$1_a$2_d$3.json 2> $O/r2_lazy_c$1_a$2_d$3.err
+  SFEM_LAZY_CHUNK=$1 SFEM_LAZY_AHEAD=$2 SFEM_LAZY_MAX_AHEAD=$3 SFEM_LAZY_DUTY=$4 timeout 600 $B > $O/r2_lazy_c$1_a$2_m$3_d$4.json 2> $O/r2_lazy_c$1_a$2_m$3_d$4.err
 done
 for f in $O/r2_lazy_*.json; do python - "$f" <<'PY'
 import json,sys
