@@ -244,36 +244,6 @@ int sfem_op_diag(const sfem_op* op, double lambda, double mu, void* diag,
  * available), 1 = force the generic runtime-(N,Q) kernel.  For tests.       */
 int sfem_op_set_variant(sfem_op* op, int32_t variant);
 
-/* Lazy zero fill of y's shared-dof prefix for the 3-D fused apply (one
- * component, not partitioned).  The scatter of poisson.py:141-146 /
- * gather_scatter.py:130-133 is a zero-initialised scatter-add; the kernel
- * accumulates shared dofs with RED, so they must be zero first.  Instead of
- * filling the whole prefix before the launch (3 DRAM accesses per shared dof:
- * zeros written, evicted, re-fetched by the first RED), the CTA steps of
- * element chunk c zero the dofs that chunk c + lookahead touches FIRST, while
- * they are still L2-resident when the REDs arrive.
- *   sfem_op_step_elems: elements per CTA step.  A chunk is `chunk_steps`
- *     consecutive steps.
- *   pieces (device int2[num_pieces]): {start, len | chunk << 8}, len <= 128,
- *     sorted by the chunk that touches the dofs first; the first `num_eager`
- *     (dofs of chunks < lookahead, or touched by no element) are zeroed before
- *     the launch; chunk_ptr (device int32[num_chunks + 1]) = first piece of
- *     every chunk.  All pieces together cover [0, sfem_op_num_zero) exactly
- *     once.  Inside the kernel the pieces are a work queue: every
- *     `duty_every`-th step of a CTA claims and zeroes `batch` pieces, at most
- *     `max_ahead` chunks ahead of its own position.  Tables are retained (not
- *     copied); chunk_ptr = NULL switches back to the eager fill.  At most 8
- *     applies of one handle may be in flight at once in this mode. */
-int32_t sfem_op_step_elems(const sfem_op* op);
-/* Length of the prefix y[0 .. n) that holds every dof touched by more than one
- * element (or by none): what an apply zeroes before accumulating. */
-int64_t sfem_op_num_zero(const sfem_op* op);
-int sfem_op_set_lazy_zero(sfem_op* op, const void* pieces, int32_t num_pieces,
-                          int32_t num_eager, const int32_t* chunk_ptr,
-                          int32_t num_chunks, int32_t chunk_steps,
-                          int32_t lookahead, int32_t max_ahead,
-                          int32_t duty_every, int32_t batch);
-
 /* ------------------------------------------------------------------------ */
 /* Peer-memory halo exchange (partitioned QQ^T over NVLink P2P stores)       */
 /* ------------------------------------------------------------------------ */

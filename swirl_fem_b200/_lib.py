@@ -146,11 +146,6 @@ SIGNATURES = {
                                            _c_ptr, _c_i32, _c_ptr]),
     'sfem_op_diag': (ctypes.c_int, [_c_ptr, _c_f64, _c_f64, _c_ptr, _c_ptr]),
     'sfem_op_set_variant': (ctypes.c_int, [_c_ptr, _c_i32]),
-    'sfem_op_step_elems': (_c_i32, [_c_ptr]),
-    'sfem_op_num_zero': (_c_i64, [_c_ptr]),
-    'sfem_op_set_lazy_zero': (ctypes.c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32,
-                                             _c_ptr, _c_i32, _c_i32, _c_i32,
-                                             _c_i32, _c_i32, _c_i32]),
     'sfem_cg_workspace_bytes': (_c_i64, [ctypes.c_int, _c_i64]),
     'sfem_cg': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr,
                                ctypes.POINTER(CgParams), _c_ptr,

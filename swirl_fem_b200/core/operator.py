@@ -76,62 +76,6 @@ class FusedOperator:
     self.handle = handle
     self.num_nodes = mesh.num_nodes
     self.ndim = mesh.ndim
-    self._lazy = None
-    # Large 3-D meshes: zero y's shared-dof prefix lazily inside the apply
-    # kernel (SFEM_LAZY_ZERO=0 keeps the eager fill, =1 forces the tables).
-    import os  # pylint: disable=g-import-not-at-top
-    mode = os.environ.get('SFEM_LAZY_ZERO', 'auto')
-    if mode != '0' and mesh.ndim == 3 and interp.collocated:
-      nz = int(lib.sfem_op_num_zero(self.handle))
-      if mode == '1' or nz * esz >= (64 << 20):
-        self.enable_lazy_zero(
-            chunk_elems=int(os.environ.get('SFEM_LAZY_CHUNK', 512)),
-            lookahead=int(os.environ.get('SFEM_LAZY_AHEAD', 2)),
-            max_ahead=int(os.environ.get('SFEM_LAZY_MAX_AHEAD', 4)),
-            duty_every=int(os.environ.get('SFEM_LAZY_DUTY', 32)))
-
-  def enable_lazy_zero(self, chunk_elems: int = 512, lookahead: int = 2,
-                       max_ahead: int = 4, duty_every: int = 32,
-                       batch: int | None = None, piece: int = 128) -> bool:
-    """Builds the tables of the lazy zero fill (`sfem_op_set_lazy_zero`).
-
-    The elements are cut into chunks of ~`chunk_elems` (a whole number of CTA
-    steps); every shared dof belongs to the chunk that touches it first; the
-    dofs are cut into pieces of at most `piece` consecutive ids, sorted by
-    that chunk.  Pieces of chunks < `lookahead` are zeroed before the launch;
-    inside the kernel every `duty_every`-th step of a CTA claims and zeroes
-    `batch` pieces (default: 1.5 x the average number of pieces per
-    `duty_every` steps, so the queue stays ahead of the elements), at most
-    `max_ahead` chunks ahead.  Index arithmetic only (torch on the device,
-    set-up time).  Returns False -- and leaves the eager fill in place -- when
-    the mesh has too few chunks.
-    """
-    lib = _lib.lib()
-    epb = int(lib.sfem_op_step_elems(self.handle))
-    tables = lazy_zero_tables(
-        self.mesh.elements, self.num_nodes,
-        int(lib.sfem_op_num_zero(self.handle)), epb, chunk_elems, lookahead,
-        piece)
-    if tables is None:
-      return False
-    pieces, num_eager, chunk_ptr, chunk_steps = tables
-    num_pieces = int(pieces.shape[0])
-    num_steps = -(-self.mesh.num_elements // epb)
-    if batch is None:
-      batch = max(2, -(-3 * num_pieces * duty_every // (2 * num_steps)))
-    _lib._check(lib.sfem_op_set_lazy_zero(
-        self.handle, _lib.ptr(pieces), num_pieces, int(num_eager),
-        _lib.ptr(chunk_ptr), int(chunk_ptr.numel() - 1), int(chunk_steps),
-        int(lookahead), int(max(max_ahead, lookahead)), int(duty_every),
-        int(batch)), 'sfem_op_set_lazy_zero')
-    self._lazy = (pieces, chunk_ptr)   # the C side retains these pointers
-    return True
-
-  def disable_lazy_zero(self):
-    _lib._check(_lib.lib().sfem_op_set_lazy_zero(
-        self.handle, None, 0, 0, None, 0, 1, 1, 1, 1, 1),
-                'sfem_op_set_lazy_zero')
-    self._lazy = None
 
   def __del__(self):
     h = getattr(self, 'handle', None)
@@ -271,62 +215,6 @@ class FusedOperator:
   def bind(self, lam: float = 0.0, mu: float = 1.0):
     """Returns the callable `A(u)` for these coefficients (for `linalg.cg`)."""
     return BoundOperator(self, lam, mu)
-
-
-def lazy_zero_tables(elements: torch.Tensor, num_nodes: int, num_zero: int,
-                     epb: int, chunk_elems: int, lookahead: int, piece: int):
-  """Tables of the lazy zero fill (see `sfem_op_set_lazy_zero`).
-
-  Returns `(pieces int32 (P, 2) = {start, len | chunk << 8}, num_eager,
-  chunk_ptr int32 (num_chunks + 1,), chunk_steps)` or None when the mesh is
-  too small.  Pieces are sorted by the chunk that touches their dofs first
-  (dofs no element touches come first, with the eager ones); a piece never
-  crosses a chunk boundary or a gap in the ids.  Works on any device (index
-  arithmetic only)."""
-  E, n = int(elements.shape[0]), int(elements.shape[1])
-  if epb <= 0 or num_zero <= 0 or num_nodes >= 2 ** 31 or piece > 255:
-    return None
-  S = max(1, int(round(chunk_elems / epb)))            # steps per chunk
-  num_steps = -(-E // epb)
-  num_chunks = -(-num_steps // S)
-  if num_chunks < lookahead + 2 or num_chunks >= (1 << 23):
-    return None
-  dev = elements.device
-  big = torch.iinfo(torch.int32).max
-  nz = int(num_zero)
-  flat = elements.reshape(-1).long()
-  chunk = (torch.arange(E, device=dev) // (S * epb)).repeat_interleave(n)
-  sel = (flat >= 0) & (flat < nz)
-  first = torch.full((nz,), big, dtype=torch.int64, device=dev)
-  first.scatter_reduce_(0, flat[sel], chunk[sel], 'amin', include_self=True)
-  del flat, chunk, sel
-  first = torch.where(first == big, torch.full_like(first, -1), first)
-  order = torch.argsort(first, stable=True)            # ids by chunk, then id
-  st = first[order]
-  # position of the first dof of chunk c in `order` (c = -1 first)
-  bounds = torch.searchsorted(
-      st, torch.arange(-1, num_chunks + 1, device=dev, dtype=st.dtype))
-  cut = torch.zeros(nz + 1, dtype=torch.bool, device=dev)
-  cut[0] = True
-  cut[1:nz] = order[1:] != order[:-1] + 1               # gaps in the ids
-  cut[bounds.clamp(max=nz)] = True                      # chunk boundaries
-  seg_start = torch.nonzero(cut[:nz]).reshape(-1)
-  seg_end = torch.cat([seg_start[1:], torch.tensor([nz], device=dev)])
-  npieces = (seg_end - seg_start + piece - 1) // piece
-  seg_of_piece = torch.repeat_interleave(
-      torch.arange(seg_start.numel(), device=dev), npieces)
-  first_piece = torch.cumsum(npieces, 0) - npieces
-  k = torch.arange(seg_of_piece.numel(), device=dev) - first_piece[seg_of_piece]
-  pos = seg_start[seg_of_piece] + k * piece
-  plen = torch.minimum(torch.full_like(pos, piece),
-                       seg_end[seg_of_piece] - pos)
-  pchunk = st[pos].clamp(min=0)                         # (-1 -> 0: eager anyway)
-  pieces = torch.stack([order[pos], plen + (pchunk << 8)],
-                       dim=1).to(torch.int32).contiguous()
-  # first piece of chunk c = number of pieces starting before its first dof
-  chunk_ptr = torch.searchsorted(pos, bounds[1:]).to(torch.int32).contiguous()
-  num_eager = int(chunk_ptr[min(lookahead, num_chunks)])
-  return pieces, num_eager, chunk_ptr, S
 
 
 class HostPipeline:

@@ -35,8 +35,6 @@ int launch_diag_generic(const sfem_op&, double, double, void*, cudaStream_t);
 template <typename T, int DIM>
 int launch_apply_colloc_dim(const sfem_op&, double, double, const void*, void*,
                             int, bool, double*, cudaStream_t);
-template <typename T>
-int step_elems_3d(int n1d, bool mass);
 int pack_connectivity(const sfem_space_desc& desc, int n,
                       const uint8_t* dirichlet, uint32_t* conn,
                       int64_t* n_zero, cudaStream_t stream);
@@ -154,11 +152,8 @@ int op_apply_internal(const sfem_op* op, double lambda, double mu,
                    d.dim == 3 && d.n1d <= 16 && (op->n_zero > 0 || dot_xy) &&
                    esz * (size_t)op->n_zero * ncomp <= ((size_t)64 << 20);
   sfem_op sub = *op;
-  sub.prezeroed = prezeroed;
   if (prezeroed) {
     sub.pdl = false;
-  } else if (lazy_zero_applicable(sub, ncomp)) {
-    sub.pdl = false;  // the 3-D launcher fills (lazily) itself
   } else if (pdl) {
     int rc = launch_zero_fill(y, esz * (size_t)op->n_zero * ncomp, dot_xy,
                               stream, &sub.pdl);
@@ -178,14 +173,6 @@ int op_apply_internal(const sfem_op* op, double lambda, double mu,
 }
 
 }  // namespace sfem
-
-static void lazy_release(sfem_op* op) {
-  op->lazy_chunk_ptr = nullptr;
-  if (op->lazy_counters) cudaFree(op->lazy_counters);
-  op->lazy_counters = nullptr;
-  delete op->lazy_seq;
-  op->lazy_seq = nullptr;
-}
 
 extern "C" {
 
@@ -333,61 +320,8 @@ int sfem_op_create(const sfem_space_desc* desc, const uint8_t* dirichlet,
 
 void sfem_op_destroy(sfem_op* op) {
   if (!op) return;
-  lazy_release(op);
   sfem::space_base_free(&op->base);
   delete op;
-}
-
-int64_t sfem_op_num_zero(const sfem_op* op) { return op ? op->n_zero : -1; }
-
-int32_t sfem_op_step_elems(const sfem_op* op) {
-  using namespace sfem;
-  if (!op) return 0;
-  const sfem_space_desc& d = op->base.desc;
-  if (d.dim != 3 || !d.collocated || d.n1d > 16) return 0;
-  return d.dtype == SFEM_F64 ? step_elems_3d<double>(d.n1d, op->with_mass != 0)
-                             : step_elems_3d<float>(d.n1d, op->with_mass != 0);
-}
-
-int sfem_op_set_lazy_zero(sfem_op* op, const void* pieces, int32_t num_pieces,
-                          int32_t num_eager, const int32_t* chunk_ptr,
-                          int32_t num_chunks, int32_t chunk_steps,
-                          int32_t lookahead, int32_t max_ahead,
-                          int32_t duty_every, int32_t batch) {
-  using namespace sfem;
-  SFEM_REQUIRE(op, "null argument");
-  lazy_release(op);
-  if (chunk_ptr == nullptr) return SFEM_OK;  // switched off
-  const int epb = sfem_op_step_elems(op);
-  SFEM_REQUIRE(epb > 0, "lazy zero fill: 3-D collocated operators only");
-  const int64_t E = op->base.desc.num_elements;
-  const int64_t num_steps = (E + epb - 1) / epb;
-  SFEM_REQUIRE(pieces != nullptr && num_pieces >= 0 && num_eager >= 0 &&
-                   num_eager <= num_pieces,
-               "lazy zero fill: bad piece table");
-  SFEM_REQUIRE(chunk_steps >= 1 && duty_every >= 1 && batch >= 1 &&
-                   lookahead >= 1 && max_ahead >= lookahead,
-               "lazy zero fill: bad chunking");
-  SFEM_REQUIRE(num_chunks == (num_steps + chunk_steps - 1) / chunk_steps,
-               "lazy zero fill: chunk table does not match the step count");
-  SFEM_REQUIRE(op->base.desc.num_nodes < ((int64_t)1 << 31) &&
-                   num_chunks < (1 << 23),
-               "lazy zero fill: ids / chunk ids out of range");
-  const size_t words = (size_t)8 * ((size_t)num_chunks + 2);
-  SFEM_CUDA_CHECK(cudaMalloc(&op->lazy_counters, words * sizeof(unsigned)));
-  op->lazy_seq = new std::atomic<unsigned>(0);
-  op->lazy_pieces = (const int2*)pieces;
-  op->lazy_chunk_ptr = chunk_ptr;
-  op->lazy_num_pieces = num_pieces;
-  op->lazy_num_eager = num_eager;
-  op->lazy_epb = epb;
-  op->lazy_chunk_steps = chunk_steps;
-  op->lazy_duty_every = duty_every;
-  op->lazy_batch = batch;
-  op->lazy_lookahead = lookahead;
-  op->lazy_max_ahead = max_ahead;
-  op->lazy_num_chunks = num_chunks;
-  return SFEM_OK;
 }
 
 int sfem_op_set_variant(sfem_op* op, int32_t variant) {

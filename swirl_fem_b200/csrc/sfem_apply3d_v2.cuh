@@ -245,12 +245,8 @@ __device__ __forceinline__ void bulk_copy_g2s_evict_first(void* smem_dst,
 //          of the next element's connectivity, a DRAM load issued only one
 //          barrier earlier);
 //   EVICT: factors staged with the evict-first copy above.
-// LAZY: y's shared-dof prefix is zeroed inside the kernel, a few chunks of
-// elements ahead of its first use (LazyDev, sfem_common.cuh); needs all CTAs
-// co-resident (cooperative launch) and ncomp == 1.
 template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH,
-          bool HALO = false, bool CONN2 = false, bool EVICT = false,
-          bool LAZY = false>
+          bool HALO = false, bool CONN2 = false, bool EVICT = false>
 __global__ void __launch_bounds__((Cfg3DV2<T, N, EPB, MINB, KCH>::threads),
                                   MINB)
 apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
@@ -258,8 +254,7 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
                   const T* __restrict__ gf, T lambda, T mu,
                   const T* __restrict__ x, T* __restrict__ y, int ncomp,
                   int64_t E, double* __restrict__ dot_xy,
-                  const __grid_constant__ HaloDev hd,
-                  const __grid_constant__ LazyDev lz) {
+                  const __grid_constant__ HaloDev hd) {
   using C = Cfg3DV2<T, N, EPB, MINB, KCH>;
   constexpr int P = C::P, n = C::n, epb = C::epb;
   constexpr int S0 = C::S0, R = C::R;
@@ -385,85 +380,12 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       nrc_c[k] = a1 ? ld_stream(conn + e1 * n + k * P + t) : kConnSentinel;
   }
 
-  // LAZY (work queue, see LazyDev): chunk of the current step kept
-  // incrementally; this CTA's own step counter selects its duty steps
-  int lz_r = 0, lz_c = 0, lz_own = 0;
-  unsigned lz_base = 0xffffffffu;  // thread 0: claim issued at the last duty
-                                   // step (none yet)
-  unsigned lz_head = 0;            // thread 0: lower bound of the queue head
-  __shared__ unsigned s_lz[2];     // [0] claimed base, [1] "this step waits"
-  auto lz_zero_batch = [&](unsigned base) {
-    // pieces [base, base + batch): a warp takes groups of 8 consecutive pieces
-    // (descriptors loaded together, coalesced zero stores), fences ONCE after
-    // its last store, and only then counts its pieces on their chunks' counters
-    // (lane j counts the j-th piece of a group)
-    const unsigned end =
-        base + (unsigned)lz.batch < (unsigned)lz.num_pieces
-            ? base + (unsigned)lz.batch
-            : (unsigned)lz.num_pieces;
-    const unsigned w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int lane = (int)(threadIdx.x & 31);
-    for (unsigned r0 = base + w * 8u; r0 < end; r0 += nw * 8u) {
-      int2 pcs[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        pcs[j] = r0 + j < end ? __ldg(lz.pieces + r0 + j) : make_int2(0, 0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int len = pcs[j].y & 0xff;
-        for (int i = lane; i < len; i += 32) y[pcs[j].x + i] = T(0);
-      }
-    }
-    __threadfence();
-    __syncwarp();
-    for (unsigned r0 = base + w * 8u; r0 < end; r0 += nw * 8u) {
-      if (lane < 8 && r0 + lane < end) {
-        const int2 pc = __ldg(lz.pieces + r0 + lane);
-        red_add_u32(lz.counters + (pc.y >> 8), 1u);
-      }
-    }
-  };
-  if constexpr (LAZY) {
-    lz_c = (int)blockIdx.x / lz.chunk_steps;
-    lz_r = (int)blockIdx.x - lz_c * lz.chunk_steps;
-  }
-
   int buf = 0;
   for (; blk < nblocks; blk += gridDim.x, buf ^= 1) {
     T* sU = sU0 + buf * C::tile;
     T* sUn = sU0 + (buf ^ 1) * C::tile;
     // ---- pipeline: next element's factors -> L2, connectivity -> registers
     const int64_t blk_n = blk + gridDim.x;
-    // LAZY: poll the counter of this step's chunk now, look at it before the
-    // scatter; on a duty step publish the claim issued one duty step ago and
-    // issue the next one (its result is not needed before the next duty step)
-    unsigned lz_seen = 0, lz_need = 0;
-    const bool lz_duty = LAZY && (lz_own % lz.duty_every) == 0;
-    if constexpr (LAZY) {
-      if (threadIdx.x == 0) {
-        if (lz_c >= lz.lookahead) {
-          lz_need = (unsigned)(__ldg(lz.chunk_ptr + lz_c + 1) -
-                               __ldg(lz.chunk_ptr + lz_c));
-          lz_seen = ld_relaxed_gpu(lz.counters + lz_c);
-        }
-        if (lz_duty) {
-          s_lz[0] = lz_base;  // visible after the barrier below
-          // keep the queue at most `max_ahead` chunks ahead of this CTA (the
-          // last returned base is a lower bound of the queue head)
-          const int c_lim = lz_c + lz.max_ahead < lz.num_chunks
-                                ? lz_c + lz.max_ahead
-                                : lz.num_chunks;
-          const unsigned limit = (unsigned)__ldg(lz.chunk_ptr + c_lim);
-          const bool below = lz_head < limit;
-          lz_base = 0xffffffffu;
-          if (below) {
-            lz_base = atomicAdd(lz.counters + lz.num_chunks + 1,
-                                (unsigned)lz.batch);
-            lz_head = lz_base;  // (used only after it has arrived)
-          }
-        }
-      }
-    }
     const int64_t e_n = blk_n * epb + slot;
     const bool active_n = lane_ok && blk_n < nblocks && e_n < E;
     uint32_t nrc[N];
@@ -526,14 +448,6 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     // ---- u tile of this element has landed (cp.async issued one element ago)
     cp_async_wait_all();
     __syncthreads();
-
-    if constexpr (LAZY) {
-      // duty step: zero the batch claimed one duty step ago
-      if (lz_duty) {
-        const unsigned base = s_lz[0];
-        if (base < (unsigned)lz.num_pieces) lz_zero_batch(base);
-      }
-    }
 
     if (HALO) {
       if (hstate == kHIface && blk >= hd.n_if_blocks) {
@@ -695,56 +609,7 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
 #pragma unroll
       for (int j = 0; j < N; ++j) sB[baseC + (SWZ ? (j ^ qs) : j)] = out[j];
     }
-    if constexpr (LAZY) {
-      // the dofs this step scatters into are zero once every piece of its
-      // chunk has been counted (normally long ago)
-      if (threadIdx.x == 0) {
-        if (lz_seen < lz_need) lz_seen = ld_relaxed_gpu(lz.counters + lz_c);
-        s_lz[1] = lz_seen < lz_need;
-      }
-    }
     __syncthreads();
-    if constexpr (LAZY) {
-      // not yet: HELP -- claim and zero batches until the chunk is complete (a
-      // CTA that only waited could wait for pieces nobody has claimed yet);
-      // bounded (~2 s): inconsistent tables must not hang the device
-      if (s_lz[1]) {
-        uint64_t t0 = 0;
-        for (unsigned spins = 0;; ++spins) {
-          __syncthreads();
-          if (threadIdx.x == 0) {
-            // first the batch this CTA still holds from its last duty step (a
-            // waiting CTA must not sit on claimed pieces), then new ones
-            if (lz_base != 0xffffffffu) {
-              s_lz[0] = lz_base;
-              lz_base = 0xffffffffu;
-            } else {
-              s_lz[0] = atomicAdd(lz.counters + lz.num_chunks + 1,
-                                  (unsigned)lz.batch);
-            }
-          }
-          __syncthreads();
-          const unsigned base = s_lz[0];
-          if (base < (unsigned)lz.num_pieces) lz_zero_batch(base);
-          __syncthreads();
-          if (threadIdx.x == 0) {
-            bool done = ld_relaxed_gpu(lz.counters + lz_c) >= lz_need;
-            if (!done && (spins & 63u) == 63u) {
-              uint64_t now;
-              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-              if (t0 == 0) t0 = now;
-              if (now - t0 > 2000000000ull) {
-                atomicExch(lz.counters + lz.num_chunks, 1u);
-                done = true;
-              }
-            }
-            s_lz[1] = !done;
-          }
-          __syncthreads();
-          if (!s_lz[1]) break;
-        }
-      }
-    }
 
     // ---- phase 5 (mapping A): sum the three parts, scatter
     if (first_step) {
@@ -780,14 +645,6 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     // in-flight cp.async targets the OTHER u tile).
     e = e_n;
     active = active_n;
-    if constexpr (LAZY) {
-      ++lz_own;
-      lz_r += (int)gridDim.x;
-      while (lz_r >= lz.chunk_steps) {
-        lz_r -= lz.chunk_steps;
-        ++lz_c;
-      }
-    }
 #pragma unroll
     for (int k = 0; k < N; ++k) rc[k] = nrc[k];
     if (HALO && hstate == kHIface && blk_n >= hd.n_if_blocks) __threadfence();
@@ -841,35 +698,8 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
   }
 }
 
-// Pre-launch part of the lazy zero fill: the ranges chunks 0 .. L-1 touch first
-// (and dofs no element touches), the chunk counters and the dot accumulator.
-template <typename T>
-__global__ void __launch_bounds__(256)
-zero_ranges_kernel(T* __restrict__ y, const int2* __restrict__ ranges,
-                   int num_ranges, unsigned* __restrict__ counters,
-                   int num_chunks, double* __restrict__ dot_xy) {
-  // one warp per piece (<= 128 dofs; the chunk id sits above bit 8 of .y)
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int r = warp; r < num_ranges; r += nwarps) {
-    const int2 rg = __ldg(ranges + r);
-    const int len = rg.y & 0xff;
-    for (int i = threadIdx.x & 31; i < len; i += 32) y[rg.x + i] = T(0);
-  }
-  if (blockIdx.x == 0) {
-    // chunk counters and the timeout flag to 0, the queue head to the first
-    // piece that is not zeroed here
-    for (int i = threadIdx.x; i <= num_chunks; i += blockDim.x) counters[i] = 0u;
-    if (threadIdx.x == 0) {
-      counters[num_chunks + 1] = (unsigned)num_ranges;
-      if (dot_xy) *dot_xy = 0.0;
-    }
-  }
-}
-
 template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH,
-          bool HALO = false, bool CONN2 = false, bool EVICT = false,
-          bool LAZY = false>
+          bool HALO = false, bool CONN2 = false, bool EVICT = false>
 int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
                     void* y, int ncomp, double* dot_xy, cudaStream_t stream) {
   using C = Cfg3DV2<T, N, EPB, MINB, KCH>;
@@ -879,8 +709,8 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
       ((size_t)C::stage_off(C::epb) +
        (KCH == 0 ? (size_t)C::epb * (MASS ? 7 : 6) * C::n : 0)) *
       sizeof(T);
-  auto kernel = apply3d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB, KCH, HALO, CONN2,
-                                  EVICT, LAZY>;
+  auto kernel =
+      apply3d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB, KCH, HALO, CONN2, EVICT>;
   static int per_sm_dev[64] = {};
   int& per_sm = per_device_slot(per_sm_dev);
   if (per_sm == 0) {
@@ -923,70 +753,10 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
     hd = f;
     hd.n_if_blocks = (hd.n_if_blocks + C::epb - 1) / C::epb;
   }
-  LazyDev lz{};
-  if constexpr (LAZY) {
-    // eager part + counters, then the kernel as a cooperative launch (its
-    // chunk counters need every CTA resident); any failure falls back to the
-    // eager fill + the ordinary kernel
-    static_assert(!HALO && !LOCAL, "lazy zero fill: plain global apply only");
-    // one of the handle's 8 counter blocks (launches of one handle may overlap
-    // on different streams: up to 8 in flight)
-    unsigned* counters = nullptr;
-    const bool ok = op.lazy_epb == EPB && op.lazy_counters && op.lazy_seq;
-    if (ok) {
-      const unsigned slot = op.lazy_seq->fetch_add(1u) & 7u;
-      counters = op.lazy_counters + (size_t)slot * ((size_t)op.lazy_num_chunks + 2);
-      int zb = (op.lazy_num_eager + 7) / 8;
-      if (zb < 1) zb = 1;
-      if (zb > num_sms() * 8) zb = num_sms() * 8;
-      zero_ranges_kernel<T><<<zb, 256, 0, stream>>>(
-          (T*)y, op.lazy_pieces, op.lazy_num_eager, counters,
-          op.lazy_num_chunks, dot_xy);
-      g_launch_count.fetch_add(1, std::memory_order_relaxed);
-      lz.pieces = op.lazy_pieces;
-      lz.chunk_ptr = op.lazy_chunk_ptr;
-      lz.counters = counters;
-      lz.chunk_steps = op.lazy_chunk_steps;
-      lz.duty_every = op.lazy_duty_every;
-      // a warp zeroes groups of 8 pieces: keep a batch within a few groups
-      lz.batch = op.lazy_batch < 32 * (C::threads / 32)
-                     ? op.lazy_batch
-                     : 32 * (C::threads / 32);
-      lz.lookahead = op.lazy_lookahead;
-      lz.max_ahead = op.lazy_max_ahead;
-      lz.num_chunks = op.lazy_num_chunks;
-      lz.num_pieces = op.lazy_num_pieces;
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = grid;
-      cfg.blockDim = dim3(C::threads);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeCooperative;
-      attr[0].val.cooperative = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      const cudaError_t e = cudaLaunchKernelEx(
-          &cfg, kernel, dm, (const uint32_t*)op.conn, (const T*)op.geom,
-          (T)lambda, (T)mu, (const T*)x, (T*)y, ncomp, E, dot_xy, hd, lz);
-      if (e == cudaSuccess) {
-        SFEM_LAUNCH_CHECK();
-        return SFEM_OK;
-      }
-    }
-    cudaGetLastError();  // clear; fall back to the eager fill
-    const size_t esz = sizeof(T);
-    if (op.n_zero > 0)
-      SFEM_CUDA_CHECK(cudaMemsetAsync(y, 0, esz * (size_t)op.n_zero, stream));
-    if (dot_xy)
-      SFEM_CUDA_CHECK(cudaMemsetAsync(dot_xy, 0, sizeof(double), stream));
-    return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, MINB, KCH, HALO, CONN2, EVICT,
-                           false>(op, lambda, mu, x, y, ncomp, dot_xy, stream);
-  }
   SFEM_CUDA_CHECK(launch_maybe_pdl(
       op.pdl, kernel, grid, dim3(C::threads), smem, stream, dm, op.conn,
       (const T*)op.geom, (T)lambda, (T)mu, (const T*)x, (T*)y, ncomp, E,
-      dot_xy, hd, lz));
+      dot_xy, hd));
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }
@@ -1120,22 +890,9 @@ int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
   }
 #endif
   using Tn = Tune3D<T, N>;
-  if constexpr (!LOCAL) {
-    if (lazy_zero_applicable(op, ncomp))
-      return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
-                             Tn::conn2, Tn::evict, true>(op, lambda, mu, x, y,
-                                                         ncomp, dot_xy, stream);
-  }
   return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
                          Tn::conn2 && !LOCAL, Tn::evict>(
       op, lambda, mu, x, y, ncomp, dot_xy, stream);
-}
-
-// Elements per CTA step of the default 3-D configuration (the granularity of
-// the lazy zero fill's duty table).
-template <typename T, int N>
-int step_elems3d(bool mass) {
-  return mass ? default_epb3d<T, N, true>() : default_epb3d<T, N, false>();
 }
 
 // Default configuration of launch3d_v2 with the halo push fused in.

@@ -385,23 +385,6 @@ int dispatch_n(const sfem_op& op, double lambda, double mu, const void* x,
 
 }  // namespace
 
-// Elements per CTA step of the default 3-D kernel for (T, n1d, mass); 0 if
-// there is no specialised kernel.
-template <typename T>
-int step_elems_3d(int n1d, bool mass) {
-  switch (n1d) {
-#define SFEM_CASE(NN) \
-  case NN:            \
-    return step_elems3d<T, NN>(mass);
-    SFEM_CASE(2) SFEM_CASE(3) SFEM_CASE(4) SFEM_CASE(5) SFEM_CASE(6)
-    SFEM_CASE(7) SFEM_CASE(8) SFEM_CASE(9) SFEM_CASE(10) SFEM_CASE(11)
-    SFEM_CASE(12) SFEM_CASE(13) SFEM_CASE(14) SFEM_CASE(15) SFEM_CASE(16)
-#undef SFEM_CASE
-    default:
-      return 0;
-  }
-}
-
 // Returns SFEM_ERR_UNSUPPORTED when no specialised kernel exists (the caller
 // then uses the generic kernel).
 template <typename T, int DIM>

@@ -5,5 +5,4 @@ namespace sfem {
 template int launch_apply_colloc_dim<float, 3>(const sfem_op&, double, double,
                                                const void*, void*, int, bool,
                                                double*, cudaStream_t);
-template int step_elems_3d<float>(int, bool);
 }  // namespace sfem

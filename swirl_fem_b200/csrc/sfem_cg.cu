@@ -429,11 +429,7 @@ int cg_iterate_impl(const sfem_op* op, sfem_halo* halo,
                     void* p, void* Ap, const void* minv, const uint8_t* owned,
                     CgState* st, int iters, cudaStream_t stream) {
   const int64_t n = op->base.desc.num_nodes * (int64_t)ncomp;
-  // lazy zero fill (large 3-D meshes): the apply zeroes its shared-dof prefix
-  // itself, just ahead of use, so the step kernel must not fill it (the fill
-  // would only be evicted again before the apply's REDs arrive)
-  const bool lazy = halo == nullptr && lazy_zero_applicable(*op, ncomp);
-  const int64_t n_zero = lazy ? 0 : op->n_zero * (int64_t)ncomp;
+  const int64_t n_zero = op->n_zero * (int64_t)ncomp;
   for (int it = 0; it < iters; ++it) {
     int rc;
     if (halo) {
@@ -443,7 +439,7 @@ int cg_iterate_impl(const sfem_op* op, sfem_halo* halo,
       if (!rc) rc = sfem_halo_wait_unpack(halo, Ap, (sfem_stream_t)stream);
     } else {
       rc = op_apply_internal(op, lambda, mu, p, Ap, ncomp, &st->pAp, stream,
-                             it > 0 && !lazy);
+                             it > 0);
     }
     if (rc) return rc;
     rc = launch_cg_step<T>(n, x, r, p, Ap, minv, owned, st, sx, n_zero, stream);

@@ -396,53 +396,6 @@ __device__ __forceinline__ bool scalar_allreduce_warp(const ScalarDev& sx,
   return ok;
 }
 
-// ---- lazy zero fill of y's shared-dof prefix (3-D fused apply) ------------------
-// The shared dofs of y are accumulated with RED, so they must be zero first.
-// Filling the whole prefix before the launch costs three DRAM accesses per
-// shared dof instead of one: the zeros are written, evicted (the prefix is
-// 320 MB at 108 M dofs, L2 is 126 MB), fetched again by the first RED and
-// written back.  Lazily, the CTA steps of element chunk c zero exactly the
-// dofs that chunk c + L touches FIRST, a few tens of MB of traffic ahead of
-// their first RED: the lines are still in L2 when the REDs arrive and go to
-// DRAM once (measured: DRAM traffic = 0.998 x the algorithmic bytes).
-//
-// Tables (host-built, sfem_op_set_lazy_zero): `pieces` = {start, len | chunk
-// << 8} node ranges of at most 128 dofs, sorted by the chunk that touches them
-// first; `chunk_ptr[c]` = first piece of chunk c.  The kernel treats them as a
-// WORK QUEUE: every `duty_every`-th step of a CTA claims `batch` pieces
-// (atomicAdd on the queue head, issued one duty step early so that its latency
-// is never waited for), zeroes them (one warp per piece, every writer fences,
-// lane 0 counts the piece on its chunk's counter) -- so the zeroing is done by
-// whichever CTAs run, in first-touch order, a few chunks ahead of the fastest
-// CTA, and a slow CTA never holds anyone up.  (Statically assigned duties --
-// chunk c zeroed by the steps of chunk c - L -- coupled every CTA to the
-// slowest one: 24-45 % slower than the eager fill,
-// profiles/r02_lazy_zero_v3_static_duty_bench.txt.)  A step scatters only
-// after counters[its chunk] == number of pieces of the chunk (relaxed poll
-// issued a step early; the REDs that follow are L2 operations issued after the
-// load returned and a block barrier, so this side needs no acquire fence); a
-// CTA that finds its chunk incomplete HELPS (claims and zeroes batches) until
-// it is, so waiting can never deadlock.
-struct LazyDev {
-  const int2* pieces;
-  const int32_t* chunk_ptr;  // (num_chunks + 1)
-  unsigned* counters;        // [0, num_chunks): pieces done per chunk;
-                             // [num_chunks]: sticky "a wait timed out";
-                             // [num_chunks + 1]: queue head (next piece)
-  int chunk_steps;           // S: chunk of a CTA step = step / S
-  int duty_every;            // a CTA claims a batch every k-th of ITS steps
-  int batch;                 // pieces per claim
-  int lookahead;             // chunks < lookahead are zeroed before the launch
-  int max_ahead;             // the queue stays <= this many chunks ahead
-  int num_chunks;
-  int num_pieces;
-};
-
-__device__ __forceinline__ void red_add_u32(unsigned* addr, unsigned v) {
-  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v)
-               : "memory");
-}
-
 // symmetric index of (i,k), i<=k, in the packed d(d+1)/2 layout
 __host__ __device__ constexpr int sym_index(int dim, int i, int k) {
   return dim == 1 ? 0
@@ -507,16 +460,6 @@ struct sfem_op {
   // set on a shallow copy by the fused CG loop: y[0 .. n_zero) and the dot
   // accumulator were already zeroed by the previous cg_step_kernel
   bool prezeroed = false;
-  // lazy zero fill (sfem_op_set_lazy_zero): device tables owned by the caller
-  const int2* lazy_pieces = nullptr;       // [0, lazy_num_eager): before launch
-  const int32_t* lazy_chunk_ptr = nullptr; // (num_chunks + 1) piece offsets
-  int lazy_num_eager = 0, lazy_num_pieces = 0;
-  int lazy_epb = 0, lazy_chunk_steps = 0, lazy_duty_every = 0, lazy_batch = 0;
-  int lazy_lookahead = 0, lazy_max_ahead = 0, lazy_num_chunks = 0;
-  // library-owned: ring of 8 counter blocks (one per launch in flight) and the
-  // launch sequence number that picks the block
-  unsigned* lazy_counters = nullptr;
-  std::atomic<unsigned>* lazy_seq = nullptr;
 };
 
 // Peer-memory all-reduce handle (sfem_halo.cu).
@@ -529,14 +472,6 @@ struct sfem_scalar_exchange {
 };
 
 namespace sfem {
-// True when the 3-D launcher zero-fills y itself (lazily, or eagerly as its own
-// fallback): the caller must not enqueue a fill.
-inline bool lazy_zero_applicable(const sfem_op& op, int ncomp) {
-  const sfem_space_desc& d = op.base.desc;
-  return op.lazy_chunk_ptr != nullptr && ncomp == 1 && op.variant == 0 &&
-         d.collocated && d.dim == 3 && d.n1d <= 16 && op.fuse == nullptr &&
-         !op.prezeroed;
-}
 inline ScalarDev scalar_view(const sfem_scalar_exchange* h) {
   ScalarDev d{};
   if (h) {

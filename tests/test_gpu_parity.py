@@ -429,59 +429,6 @@ def test_operator_apply_reoriented_hexes_fp64(n1d):
       assert rel_err(op.apply(dev(u), lam=lam, mu=mu).cpu(), want) < 1e-10
 
 
-@pytest.mark.parametrize('case', [(8, 8, torch.float64), (10, 5, torch.float64),
-                                  (10, 6, torch.float32)],
-                         ids=lambda c: f'ne{c[0]}_N{c[1]}_{str(c[2])[-7:]}')
-def test_lazy_zero_fill_matches_oracle(case):
-  """The in-kernel lazy zero fill of y's shared-dof prefix (per-chunk duty
-  ranges + chunk counters, cooperative launch) gives the eager fill's result:
-  repeated applies on a poisoned y, the dot-product epilogue, and a whole CG
-  solve (every iteration's apply fills lazily), against the oracle."""
-  from swirl_fem_b200.core.operator import JacobiPreconditioner
-  from swirl_fem_b200.linalg.cg import cg
-  ne, n1d, dtype = case
-  refined, mesh, space, oracle, bmask = _build(3, ne, n1d, GLL, n1d, dtype)
-  interior = 1.0 - bmask
-  op = space.operator(dirichlet_mask=bmask, with_mass=True)
-  rng = np.random.default_rng(n1d)
-  u = rng.standard_normal(mesh.num_nodes)
-  if dtype == torch.float32:
-    u = u.astype(np.float32).astype(np.float64)
-  ud = dev(u, dtype)
-  eager = {}
-  for lam, mu in ((0.0, 1.0), (0.7, 1.3)):
-    eager[(lam, mu)] = op.apply(ud, lam=lam, mu=mu)
-  assert op.enable_lazy_zero(chunk_elems=64, lookahead=2, max_ahead=3,
-                             duty_every=4)
-  tol = TOL[dtype]
-  for lam, mu in ((0.0, 1.0), (0.7, 1.3)):
-    want = oracle.apply(u, lam=lam, mu=mu, interior_mask=interior)
-    for rep in range(4):
-      y = torch.full_like(ud, float('nan'))      # poisoned: nothing pre-zeroed
-      dot = torch.full((), 123.0, dtype=torch.float64, device='cuda')
-      op.apply(ud, lam=lam, mu=mu, out=y, dot_out=dot)
-      assert rel_err(y.cpu(), want) < tol, (lam, mu, rep)
-      assert rel_err(y.cpu(), eager[(lam, mu)].cpu()) < (
-          1e-14 if dtype == torch.float64 else 1e-6)
-      assert abs(float(dot) - float(u @ want)) <= tol * 10 * np.abs(
-          u * want).sum()
-  if dtype == torch.float64:
-    b = op.apply(torch.ones_like(ud), lam=1.0, mu=0.0)
-    minv = op.jacobi_minv()
-    xs, info = cg(op.bind(0.0, 1.0), b, tol=1e-8, M=JacobiPreconditioner(minv),
-                  check_every=7)
-    gb = oracle.apply(np.ones(mesh.num_nodes), 1.0, 0.0, interior)
-    gd = oracle.stiffness_diag(interior)
-    gminv = np.where(gd != 0, 1.0 / np.where(gd != 0, gd, 1.0), 0.0)
-    gx, ginfo = dense.cg(lambda v: oracle.apply(v, interior_mask=interior), gb,
-                         tol=1e-8, M=lambda v: gminv * v)
-    assert abs(info['num_iterations'] - ginfo['num_iterations']) <= 1
-    assert rel_err(xs.cpu(), gx) < 1e-7
-  op.disable_lazy_zero()
-  assert rel_err(op.apply(ud).cpu(), eager[(0.0, 1.0)].cpu()) < (
-      1e-14 if dtype == torch.float64 else 1e-6)
-
-
 def test_host_pipeline_matches_resident_apply():
   """`HostPipeline` (upload / apply / download overlapped on three streams,
   double-buffered): every submitted host vector gets ITS result, in order,
