@@ -856,8 +856,8 @@ int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
         break;
     }
   }
-  // tuning variants (relative to the default), fp64 Laplacian, N = 5..9 only
-  if constexpr (sizeof(T) == 8 && N >= 5 && N <= 9 && !MASS && !LOCAL) {
+  // tuning variants (relative to the default), Laplacian, N = 5..9 only
+  if constexpr (N >= 5 && N <= 9 && !MASS && !LOCAL) {
     constexpr int Ep = clamp_int(EPB + 1, 1, 16), Em = clamp_int(EPB - 1, 1, 16);
     constexpr int E2 = clamp_int(EPB * 2, 1, 16);
     using Ap = AutoCfg3D<T, N, MASS, Ep>;
