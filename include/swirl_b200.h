@@ -364,6 +364,22 @@ int sfem_scalar_allreduce(sfem_scalar_exchange* h, double* values,
 int sfem_scalar_exchange_timed_out(const sfem_scalar_exchange* h,
                                    sfem_stream_t stream);
 
+/* Fused Stokes divergence and its transpose (StokesSEM.D / Dt,
+ * swirl_fem/navier_stokes/navier_stokes.py:313-338): ONE launch each instead
+ * of gather -> sfem_space_eval -> sfem_pointwise -> sfem_space_eval_transpose ->
+ * scatter.  `vspace`: the continuous GLL velocity space with its collocated
+ * rule (created with invjacs and jacdets); `pspace`: the pressure space on the
+ * same elements and rule.
+ *   sfem_stokes_div:    u (G_v, dim) AoS -> out (G_p,)  (zero-initialised sum)
+ *   sfem_stokes_grad_t: p (G_p,) -> out (G_v, dim), rows scaled by mask (G_v,)
+ *                       (the interior mask; NULL: none).
+ * SFEM_ERR_UNSUPPORTED when N^dim > 1024 (callers keep the composed path). */
+int sfem_stokes_div(const sfem_space* vspace, const sfem_space* pspace,
+                    const void* u, void* out, sfem_stream_t stream);
+int sfem_stokes_grad_t(const sfem_space* vspace, const sfem_space* pspace,
+                       const void* p, const void* mask, void* out,
+                       sfem_stream_t stream);
+
 /* ------------------------------------------------------------------------ */
 /* CG (swirl_fem/linalg/cg.py:30-97)                                         */
 /* ------------------------------------------------------------------------ */

@@ -130,6 +130,9 @@ SIGNATURES = {
                                                  _c_i32, _c_ptr, _c_ptr]),
     'sfem_pointwise': (ctypes.c_int, [ctypes.c_int, _c_i32, _c_i32, _c_ptr,
                                       _c_ptr, _c_i64, _c_ptr, _c_ptr]),
+    'sfem_stokes_div': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+    'sfem_stokes_grad_t': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr,
+                                          _c_ptr, _c_ptr]),
     'sfem_space_integrate': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr]),
     'sfem_op_geom_bytes': (_c_i64, [ctypes.POINTER(SpaceDesc), _c_i32]),
     'sfem_op_conn_bytes': (_c_i64, [ctypes.POINTER(SpaceDesc)]),
@@ -372,6 +375,33 @@ def pointwise(kind: int, dim: int, a, g, out):
     _check(lib().sfem_pointwise(dtype_code(out.dtype), kind, dim, ptr(a),
                                 ptr(g), npts, ptr(out),
                                 stream_ptr(out.device)), 'sfem_pointwise')
+  return out
+
+
+def stokes_div(vspace_handle, pspace_handle, u, num_pressure_nodes: int):
+  """`sfem_stokes_div`: fused D (velocity (G_v, d) -> pressure covector (G_p,)).
+  Raises NotImplementedError when the element is too large for the fused
+  kernel (the caller keeps the composed path)."""
+  require_cuda(u)
+  u = u.contiguous()
+  out = torch.empty(num_pressure_nodes, dtype=u.dtype, device=u.device)
+  with torch.cuda.device(u.device):
+    _check(lib().sfem_stokes_div(vspace_handle, pspace_handle, ptr(u), ptr(out),
+                                 stream_ptr(u.device)), 'sfem_stokes_div')
+  return out
+
+
+def stokes_grad_t(vspace_handle, pspace_handle, p, mask, num_velocity_nodes,
+                  ndim):
+  """`sfem_stokes_grad_t`: fused D^T (pressure (G_p,) -> velocity (G_v, d)),
+  rows scaled by `mask` (G_v,)."""
+  require_cuda(p, mask)
+  p = p.contiguous()
+  out = torch.empty((num_velocity_nodes, ndim), dtype=p.dtype, device=p.device)
+  with torch.cuda.device(p.device):
+    _check(lib().sfem_stokes_grad_t(vspace_handle, pspace_handle, ptr(p),
+                                    ptr(mask), ptr(out), stream_ptr(p.device)),
+           'sfem_stokes_grad_t')
   return out
 
 

@@ -382,12 +382,51 @@ class StokesSEM:
         _DIVERGENCE_FORM,
         (vs.vector_function(None), ps.scalar_function(p_local)))
 
+  def _fused_pair(self):
+    """Handles for the fused `D` / `D^T` kernels, or None when the spaces do
+    not fit them (then the composed element-local path is used)."""
+    ok = self._cache.get('fused_ddt')
+    if ok is None:
+      vs = getattr(self.velocity, 'vspace', None)
+      ps = getattr(self.pressure, 'pspace', None)
+      ok = (getattr(vs, '_handle', None) is not None and
+            getattr(ps, '_handle', None) is not None and
+            vs.mesh.ndim in (2, 3) and
+            vs.mesh.num_nodes_per_element <= 1024 and
+            vs.mesh.axis_name is None)
+      self._cache['fused_ddt'] = ok
+      if ok:
+        mask = self.velocity.interior_mask[:, 0].to(vs.dtype).contiguous()
+        self._cache['mask_vec'] = mask
+    return ok
+
   def D(self, u):
-    """Discrete divergence: velocity (G_v, d) -> pressure covector (G_p,)."""
-    return self.pressure.scatter(self.D_local(self.velocity.gather(u)))
+    """Discrete divergence: velocity (G_v, d) -> pressure covector (G_p,).
+    ONE fused launch (`sfem_stokes_div`: gather, gradient, trace with the
+    inverse Jacobian, weighted pressure-basis contraction, scatter);
+    `D_composed` is the element-local formulation of the reference."""
+    if self._fused_pair():
+      vs, ps = self.velocity.vspace, self.pressure.pspace
+      return _lib.stokes_div(vs._handle.handle, ps._handle.handle,  # pylint: disable=protected-access
+                             u.to(vs.dtype), ps.mesh.num_nodes)
+    return self.D_composed(u)
 
   def Dt(self, p):
-    """Discrete (weak) pressure gradient, the transpose of `D`, masked."""
+    """Discrete (weak) pressure gradient, the transpose of `D`, masked: ONE
+    fused launch (`sfem_stokes_grad_t`)."""
+    if self._fused_pair():
+      vs, ps = self.velocity.vspace, self.pressure.pspace
+      return _lib.stokes_grad_t(vs._handle.handle, ps._handle.handle,  # pylint: disable=protected-access
+                                p.to(vs.dtype), self._cache['mask_vec'],
+                                vs.mesh.num_nodes, vs.mesh.ndim)
+    return self.Dt_composed(p)
+
+  def D_composed(self, u):
+    """`D` as scatter(D_local(gather(u))) (navier_stokes.py:331-333)."""
+    return self.pressure.scatter(self.D_local(self.velocity.gather(u)))
+
+  def Dt_composed(self, p):
+    """`D^T` as mask * scatter(Dt_local(gather(p))) (navier_stokes.py:335-338)."""
     return self.velocity.interior_mask * self.velocity.scatter(
         self.Dt_local(self.pressure.gather(p)))
 

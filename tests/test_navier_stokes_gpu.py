@@ -311,6 +311,36 @@ def test_fixed_form_kernels_equal_the_general_form_path():
     assert rel_err(fast, general.cpu().numpy()) < 1e-13
 
 
+@pytest.mark.parametrize('ndim,ne,order', [(2, 5, 7), (2, 3, 4), (3, 2, 4),
+                                           (3, 2, 6)])
+def test_fused_div_and_gradient_match_composed(ndim, ne, order):
+  """`sfem_stokes_div` / `sfem_stokes_grad_t` (one launch each) against the
+  composed element-local formulation (evaluation -> pointwise -> transposed
+  evaluation, itself checked against the reference goldens above), 2-D and
+  3-D, curved elements, and the adjoint identity <D u, p> = <u, D^T p> on
+  interior velocities."""
+  from swirl_fem_b200.common.premesh_commons import unit_cube_mesh
+  pm = unit_cube_mesh(ne, ndim=ndim, a=-1., b=1.)
+  x = np.asarray(pm.node_coords, dtype=np.float64)
+  x = x + 0.06 * np.sin(np.pi * x[:, np.roll(np.arange(ndim), 1)]) * (1 - x ** 2)
+  sem = _sem(pm.replace(node_coords=x), order)
+  rng = np.random.default_rng(order)
+  nv = sem.velocity.mesh.num_nodes
+  npr = sem.pressure.pspace.mesh.num_nodes
+  u = dev(rng.standard_normal((nv, ndim)))
+  p = dev(rng.standard_normal(npr))
+  assert sem._fused_pair()  # pylint: disable=protected-access
+  d_f, d_c = sem.D(u), sem.D_composed(u)
+  g_f, g_c = sem.Dt(p), sem.Dt_composed(p)
+  assert d_f.shape == d_c.shape and g_f.shape == g_c.shape
+  assert rel_err(d_f, d_c.cpu().numpy()) < 1e-12
+  assert rel_err(g_f, g_c.cpu().numpy()) < 1e-12
+  ui = u * sem.velocity.interior_mask
+  lhs = float((sem.D(ui) * p).sum())
+  rhs = float((ui * sem.Dt(p)).sum())
+  assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs), 1.0)
+
+
 def test_kolmogorov_steps_match_oracle():
   """`examples/kolmogorov.solve_one_step` (niles/datagen/datagen.py:88-102)
   against the oracle over two steps on the doubly periodic square."""
