@@ -77,12 +77,26 @@ def bdfk_coeffs(k: int) -> np.ndarray:
 def _pressure_project_out_nullspace(sem, p):
   """Subtracts the constant mode (mass-weighted mean) from a pressure field;
   the preconditioner of the singular pressure system
-  (navier_stokes.py:73-78).  Both dot products are the device `sfem_dot`."""
+  (navier_stokes.py:73-78): `w - (q.B w / q.B q) q` with `q = 1`.
+
+  `B` (the pressure mass matrix) is symmetric, so `q . B w = (B q) . w`: the
+  vector `B q` and the scalar `q . B q` do not depend on `w` and are computed
+  once per `StokesSEM` (the reference re-assembles `B w` and `B q` on every
+  call, i.e. in every iteration of the pressure CG); per call this is one
+  device dot product and one fused update."""
   shared = sem.pressure.exchange(p)
-  constant = torch.ones_like(p)
-  mean = (_lib.dot(constant, sem.pressure.B(shared)) /
-          _lib.dot(constant, sem.pressure.B(constant)))
-  return shared - mean.to(p.dtype) * constant
+  cache = getattr(sem, '_cache', None)
+  key = ('nullspace', shared.dtype, shared.device)
+  entry = None if cache is None else cache.get(key)
+  if entry is None:
+    constant = torch.ones_like(shared)
+    b_const = sem.pressure.B(constant).contiguous()
+    entry = (b_const, _lib.dot(constant, b_const))
+    if cache is not None:
+      cache[key] = entry
+  b_const, norm = entry
+  mean = _lib.dot(b_const, shared.contiguous()) / norm
+  return shared - mean.to(p.dtype)
 
 
 @enum.unique
