@@ -427,9 +427,13 @@ def run_ours(args):
       halo_path = ('peer memory (in-kernel NVLink push)'
                    if halo.enable_p2p(dtype, device) else
                    'nccl all_to_all (peer mapping failed)')
-      if os.environ.get('SFEM_HALO_FUSE_UNPACK', '1') == '0':
-        halo.p2p_set_option(1, 0)
-        halo_path += ', canonical sum in the wait kernel'
+      # where the canonical sum runs: 1 in the apply kernel's own CTAs, 2 in
+      # the wait kernel concurrently with the interior elements, 0 after the
+      # apply (developer switch; the library default applies otherwise)
+      mode = os.environ.get('SFEM_HALO_FUSE_UNPACK')
+      if mode is not None:
+        halo.p2p_set_option(1, int(mode))
+        halo_path += f', canonical-sum mode {int(mode)}'
     else:
       halo_path = 'nccl all_to_all'
   torch.cuda.synchronize()

@@ -361,7 +361,9 @@ class HaloPlan:
     return p['handle']
 
   def p2p_set_option(self, key: int, value: int):
-    """0: slice size, 1: fuse the canonical sum into the apply kernel."""
+    """0: slice size; 1: where the canonical sum of a fused apply runs (0 in
+    the wait kernel after the apply, 1 in the apply kernel's own CTAs, 2 in the
+    wait kernel concurrently with the apply's interior elements)."""
     p = getattr(self, '_p2p', None)
     if p is not None and p['handle'] is not None:
       _lib._check(_lib.lib().sfem_halo_set_option(p['handle'], key, value),

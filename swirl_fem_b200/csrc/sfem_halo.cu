@@ -15,6 +15,7 @@
 // this rank raises after its unpack of epoch e (stream order), so a buffer is
 // never overwritten while it is still being read.
 
+#include <cstdlib>
 #include <cstring>
 
 #include "sfem_common.cuh"
@@ -27,7 +28,9 @@ struct sfem_halo {
   uint64_t epoch = 0;
   unsigned slice = 256;      // default work-item size (standalone kernels)
   unsigned cur_uslice = 256; // canonical-sum work-item size of this epoch
+  unsigned cur_slice = 256;  // push work-item size of this epoch
   int fuse_unpack = 1;
+  bool last_push_fused = false;  // the current epoch's push ran inside an apply
 };
 
 namespace sfem {
@@ -71,11 +74,40 @@ halo_push_kernel(const T* __restrict__ y, const __grid_constant__ HaloDev hd) {
 // this epoch, then runs whatever is left of the canonical sum (nothing, when
 // the fused apply already did it).  The last CTA to finish resets the handle's
 // counters for the next epoch.
+// `early`: the kernel was launched as a programmatic dependent of a HALO apply
+// whose CTAs do not run the canonical sum themselves: it does NOT wait for the
+// whole apply grid first -- the sum needs only this rank's pushes complete
+// (y's shared dofs final and no longer read) and the peers' flags, and no
+// interior element touches a shared dof -- so it runs on the SMs' spare warp
+// slots while the interior elements are still being computed, and waits for
+// the apply grid only at its very end (stream order for whatever follows, and
+// the counter reset).
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-halo_wait_unpack_kernel(T* __restrict__ u, const __grid_constant__ HaloDev hd) {
+halo_wait_unpack_kernel(T* __restrict__ u, const __grid_constant__ HaloDev hd,
+                        int early) {
   __shared__ unsigned s_slice;
-  pdl_wait();  // launched as a programmatic dependent of the apply kernel
+  if (!early) pdl_wait();  // programmatic dependent of the apply kernel
+  if (early) {
+    // bounded spin (thread 0) until all of this rank's push slices completed
+    if (threadIdx.x == 0) {
+      uint64_t t0 = 0;
+      unsigned spins = 0;
+      while (ld_acquire_gpu(&hd.counters[2]) < hd.num_slices) {
+        __nanosleep(100);
+        if ((++spins & 1023u) == 0) {
+          uint64_t now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          if (now - t0 > 4000000000ull) {
+            atomicExch(&hd.counters[4], 1u);
+            break;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
   // other CTAs claim slices concurrently: one thread decides for the CTA
   if (threadIdx.x == 0) s_slice = ld_relaxed_gpu(&hd.counters[5]);
   __syncthreads();
@@ -99,6 +131,7 @@ halo_wait_unpack_kernel(T* __restrict__ u, const __grid_constant__ HaloDev hd) {
     halo_unpack_slices<T>(hd, u, &s_slice);
   }
   __syncthreads();
+  if (early) pdl_wait();  // the apply grid is through: counters may be reset
   if (threadIdx.x == 0) {
     const unsigned done = atomicAdd(&hd.counters[3], 1u) + 1u;
     if (done == gridDim.x) {
@@ -124,11 +157,11 @@ HaloDev device_view(const sfem_halo* h, int64_t num_interface_elements) {
   hd.peer_flag = h->d_peer_flag;
   hd.flag_parity_off = parity ? (uint64_t)d.world * 8u : 0u;
   hd.num_peers = d.num_peers;
-  hd.slice = h->slice;
-  hd.num_slices = (unsigned)((d.num_send + h->slice - 1) / h->slice);
+  hd.slice = h->cur_slice;
+  hd.num_slices = (unsigned)((d.num_send + h->cur_slice - 1) / h->cur_slice);
   hd.uslice = h->cur_uslice;
   hd.num_uslices = (unsigned)((d.num_dofs + hd.uslice - 1) / hd.uslice);
-  hd.fuse_unpack = h->fuse_unpack;
+  hd.fuse_unpack = h->fuse_unpack == 1;
   hd.flags = d.flags + (parity ? d.world : 0);
   hd.peer_ranks = h->d_peer_ranks;
   hd.recv = (const char*)d.recv + (parity ? d.parity_stride_bytes : 0);
@@ -145,6 +178,7 @@ HaloDev device_view(const sfem_halo* h, int64_t num_interface_elements) {
 HaloDev begin_epoch(sfem_halo* h, int64_t num_interface_elements) {
   h->epoch += 1;
   h->cur_uslice = h->slice;
+  h->cur_slice = h->slice;
   return device_view(h, num_interface_elements);
 }
 
@@ -225,9 +259,12 @@ int op_apply_halo_internal(const sfem_op* op, sfem_halo* halo, double lambda,
   if (rc) {
     halo->epoch = epoch0;
     halo->cur_uslice = uslice0;
+    halo->cur_slice = halo->slice;
     return rc;
   }
   halo->cur_uslice = hd.uslice;
+  halo->cur_slice = hd.slice;  // the wait kernel counts the same push slices
+  halo->last_push_fused = true;
   return rc;
 }
 
@@ -398,7 +435,12 @@ int sfem_halo_set_option(sfem_halo* halo, int32_t key, int64_t value) {
       halo->slice = (unsigned)value;
       return SFEM_OK;
     case 1:
-      halo->fuse_unpack = value != 0;
+      // 0: canonical sum in the wait kernel after the apply; 1: in the apply
+      // kernel's own CTAs; 2: in the wait kernel, CONCURRENTLY with the apply's
+      // interior elements (it is launched as a programmatic dependent and
+      // only needs this rank's pushes and the peers' flags, not the interior)
+      SFEM_REQUIRE(value >= 0 && value <= 2, "fuse_unpack must be 0, 1 or 2");
+      halo->fuse_unpack = (int)value;
       return SFEM_OK;
     default:
       set_error("sfem_halo_set_option: unknown key");
@@ -409,6 +451,7 @@ int sfem_halo_set_option(sfem_halo* halo, int32_t key, int64_t value) {
 int sfem_halo_push(sfem_halo* halo, const void* u, sfem_stream_t stream) {
   using namespace sfem;
   SFEM_REQUIRE(halo && u, "null argument");
+  halo->last_push_fused = false;
   const HaloDev hd = begin_epoch(halo, 0);
   return push_standalone(halo, hd, u, (cudaStream_t)stream);
 }
@@ -423,18 +466,34 @@ int sfem_halo_wait_unpack(sfem_halo* halo, void* u, sfem_stream_t stream_) {
   // sized for the case that the whole sum is still to do (one slice per CTA,
   // at most 2 CTAs per SM); when the fused apply already did it the CTAs
   // return at once
+  // SFEM_WAIT_PDL=0 / SFEM_WAIT_CTAS=n: developer switches (launch the wait
+  // kernel as an ordinary dependent / cap its grid)
+  static const bool wait_pdl = [] {
+    const char* e = getenv("SFEM_WAIT_PDL");
+    return !(e && e[0] == '0');
+  }();
+  static const int wait_ctas = [] {
+    const char* e = getenv("SFEM_WAIT_CTAS");
+    return e ? atoi(e) : 0;
+  }();
   int64_t b = hd.num_uslices;
-  const int64_t cap = (int64_t)num_sms() * 2;
+  int64_t cap = (int64_t)num_sms() * 2;
+  if (wait_ctas > 0) cap = wait_ctas;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
+  // concurrent mode: only behind a fused apply of THIS epoch (the kernel then
+  // spins on counters the apply advances), one CTA per SM so that it fits the
+  // spare warp slots; never without the programmatic-dependent attribute
+  const int early = halo->fuse_unpack == 2 && halo->last_push_fused && wait_pdl;
+  if (early && b > num_sms()) b = num_sms();
   if (d.dtype == SFEM_F64)
-    SFEM_CUDA_CHECK(launch_maybe_pdl(true, halo_wait_unpack_kernel<double>,
+    SFEM_CUDA_CHECK(launch_maybe_pdl(wait_pdl, halo_wait_unpack_kernel<double>,
                                      dim3((unsigned)b), dim3(kThreads), 0,
-                                     stream, (double*)u, hd));
+                                     stream, (double*)u, hd, early));
   else
-    SFEM_CUDA_CHECK(launch_maybe_pdl(true, halo_wait_unpack_kernel<float>,
+    SFEM_CUDA_CHECK(launch_maybe_pdl(wait_pdl, halo_wait_unpack_kernel<float>,
                                      dim3((unsigned)b), dim3(kThreads), 0,
-                                     stream, (float*)u, hd));
+                                     stream, (float*)u, hd, early));
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }

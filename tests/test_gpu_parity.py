@@ -742,7 +742,13 @@ def test_peer_memory_halo_single_process(case, dtype):
   if dtype == torch.float32:
     gu = gu.astype(np.float32).astype(np.float64)
   tol = TOL[dtype]
-  for epoch, (lam, mu) in enumerate([(0.3, 1.0), (0.0, 1.0), (1.0, 0.5)]):
+  # the canonical sum in the apply kernel's own CTAs (1), in the wait kernel
+  # after the apply (0), in the wait kernel concurrently with the interior (2)
+  for epoch, (lam, mu, mode) in enumerate([
+      (0.3, 1.0, 1), (0.0, 1.0, 1), (1.0, 0.5, 0), (0.3, 1.0, 2),
+      (0.0, 1.0, 2), (1.0, 0.5, 2)]):
+    for pl in plans:
+      pl.p2p_set_option(1, mode)
     gy = oracle.apply(gu, lam=lam, mu=mu, interior_mask=1.0 - bmask)
     # every rank's apply + push first (a push never waits), then the waits
     for r in range(world):
