@@ -457,7 +457,9 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
           __threadfence();
           atomicAdd(&hd.counters[0], 1u);
         }
-        hstate = kHSignal;
+        // fuse_push == 0: the push, too, is done by the concurrently running
+        // wait kernel; this CTA's only halo duty was the signal above
+        hstate = hd.fuse_push ? kHSignal : kHDone;
         if (stamp) halo_stamp(hd, 1);
       } else if (hstate == kHSignal && s_halo[0]) {
         if (stamp) halo_stamp(hd, 2);
@@ -671,7 +673,7 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
         __threadfence();
         atomicAdd(&hd.counters[0], 1u);
       }
-      hstate = kHSignal;
+      hstate = hd.fuse_push ? kHSignal : kHDone;
     }
     if (hstate == kHSignal) {
       __syncthreads();
@@ -750,6 +752,7 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
     f.num_slices = (unsigned)((f.num_send + f.slice - 1) / f.slice);
     f.uslice = size_for(f.num_dofs);
     f.num_uslices = (unsigned)((f.num_dofs + f.uslice - 1) / f.uslice);
+    f.apply_grid = grid.x;
     hd = f;
     hd.n_if_blocks = (hd.n_if_blocks + C::epb - 1) / C::epb;
   }

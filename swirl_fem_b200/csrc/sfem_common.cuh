@@ -155,6 +155,8 @@ struct HaloDev {
   // receive side (canonical sum, see sfem_halo_unpack_canonical)
   unsigned num_uslices;       // ceil(num_dofs / slice)
   int fuse_unpack;            // fused apply: also run the canonical sum
+  int fuse_push;              // fused apply: its CTAs push the shared dofs
+  unsigned apply_grid;        // CTAs of the fused apply (counters[0] target)
   const uint64_t* flags;      // this rank's flag words of this epoch's parity
   const int32_t* peer_ranks;  // (num_peers)
   const void* recv;           // this epoch's receive buffer

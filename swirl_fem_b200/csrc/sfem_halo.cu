@@ -29,6 +29,7 @@ struct sfem_halo {
   unsigned slice = 256;      // default work-item size (standalone kernels)
   unsigned cur_uslice = 256; // canonical-sum work-item size of this epoch
   unsigned cur_slice = 256;  // push work-item size of this epoch
+  unsigned cur_grid = 0;     // CTAs of this epoch's fused apply
   int fuse_unpack = 1;
   bool last_push_fused = false;  // the current epoch's push ran inside an apply
 };
@@ -88,6 +89,28 @@ halo_wait_unpack_kernel(T* __restrict__ u, const __grid_constant__ HaloDev hd,
                         int early) {
   __shared__ unsigned s_slice;
   if (!early) pdl_wait();  // programmatic dependent of the apply kernel
+  if (early && !hd.fuse_push) {
+    // the push is ours as well: once every CTA of the apply has signalled its
+    // interface elements (bounded spin), push the shared dofs to the peers
+    if (threadIdx.x == 0) {
+      uint64_t t0 = 0;
+      unsigned spins = 0;
+      while (ld_acquire_gpu(&hd.counters[0]) < hd.apply_grid) {
+        __nanosleep(100);
+        if ((++spins & 1023u) == 0) {
+          uint64_t now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          if (now - t0 > 4000000000ull) {
+            atomicExch(&hd.counters[4], 1u);
+            break;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    halo_push_slices<T>(hd, u, &s_slice);
+  }
   if (early) {
     // bounded spin (thread 0) until all of this rank's push slices completed
     if (threadIdx.x == 0) {
@@ -162,6 +185,8 @@ HaloDev device_view(const sfem_halo* h, int64_t num_interface_elements) {
   hd.uslice = h->cur_uslice;
   hd.num_uslices = (unsigned)((d.num_dofs + hd.uslice - 1) / hd.uslice);
   hd.fuse_unpack = h->fuse_unpack == 1;
+  hd.fuse_push = h->fuse_unpack != 3;
+  hd.apply_grid = h->cur_grid;
   hd.flags = d.flags + (parity ? d.world : 0);
   hd.peer_ranks = h->d_peer_ranks;
   hd.recv = (const char*)d.recv + (parity ? d.parity_stride_bytes : 0);
@@ -264,6 +289,7 @@ int op_apply_halo_internal(const sfem_op* op, sfem_halo* halo, double lambda,
   }
   halo->cur_uslice = hd.uslice;
   halo->cur_slice = hd.slice;  // the wait kernel counts the same push slices
+  halo->cur_grid = hd.apply_grid;
   halo->last_push_fused = true;
   return rc;
 }
@@ -439,7 +465,9 @@ int sfem_halo_set_option(sfem_halo* halo, int32_t key, int64_t value) {
       // kernel's own CTAs; 2: in the wait kernel, CONCURRENTLY with the apply's
       // interior elements (it is launched as a programmatic dependent and
       // only needs this rank's pushes and the peers' flags, not the interior)
-      SFEM_REQUIRE(value >= 0 && value <= 2, "fuse_unpack must be 0, 1 or 2");
+      // 3: as 2, and the PUSH is done there too (after every CTA of the apply
+      // has signalled its interface elements): the apply's CTAs only signal
+      SFEM_REQUIRE(value >= 0 && value <= 3, "fuse_unpack must be 0..3");
       halo->fuse_unpack = (int)value;
       return SFEM_OK;
     default:
@@ -484,7 +512,7 @@ int sfem_halo_wait_unpack(sfem_halo* halo, void* u, sfem_stream_t stream_) {
   // concurrent mode: only behind a fused apply of THIS epoch (the kernel then
   // spins on counters the apply advances), one CTA per SM so that it fits the
   // spare warp slots; never without the programmatic-dependent attribute
-  const int early = halo->fuse_unpack == 2 && halo->last_push_fused && wait_pdl;
+  const int early = halo->fuse_unpack >= 2 && halo->last_push_fused && wait_pdl;
   if (early && b > num_sms()) b = num_sms();
   if (d.dtype == SFEM_F64)
     SFEM_CUDA_CHECK(launch_maybe_pdl(wait_pdl, halo_wait_unpack_kernel<double>,

@@ -714,6 +714,7 @@ def test_peer_memory_halo_single_process(case, dtype):
       r, b.interface_local, b.interface_global, gathered, b.premesh.num_nodes)
            for r, b in enumerate(blks)]
   HaloPlan.enable_p2p_local(plans, dtype, device)
+  streams = [torch.cuda.Stream(device=device) for _ in range(world)]
   # a rough field (as the random vectors of the apply tests, but a function of
   # the coordinates so that every rank sees the same values): A u of a smooth
   # u is tiny against |A| |u|, and the fp32 tolerance would measure that
@@ -743,20 +744,32 @@ def test_peer_memory_halo_single_process(case, dtype):
     gu = gu.astype(np.float32).astype(np.float64)
   tol = TOL[dtype]
   # the canonical sum in the apply kernel's own CTAs (1), in the wait kernel
-  # after the apply (0), in the wait kernel concurrently with the interior (2)
+  # after the apply (0), in the wait kernel concurrently with the interior (2),
+  # push AND sum in the concurrent wait kernel (3)
   for epoch, (lam, mu, mode) in enumerate([
       (0.3, 1.0, 1), (0.0, 1.0, 1), (1.0, 0.5, 0), (0.3, 1.0, 2),
-      (0.0, 1.0, 2), (1.0, 0.5, 2)]):
+      (0.0, 1.0, 2), (1.0, 0.5, 2), (0.3, 1.0, 3), (1.0, 0.5, 3),
+      (0.0, 1.0, 1)]):
     for pl in plans:
       pl.p2p_set_option(1, mode)
     gy = oracle.apply(gu, lam=lam, mu=mu, interior_mask=1.0 - bmask)
-    # every rank's apply + push first (a push never waits), then the waits
-    for r in range(world):
-      ops[r].apply_partitioned(us[r], ys[r], plans[r],
-                               blks[r].num_interface_elements, lam=lam, mu=mu,
-                               dot_out=dots[r], wait=False)
-    for r in range(world):
-      plans[r].p2p_wait_unpack(ys[r])
+    if mode == 3 and ndim == 3:
+      # the push lives in the wait kernel: the ranks must run concurrently
+      # (one stream each), as they do with one process per GPU
+      torch.cuda.synchronize()
+      for r in range(world):
+        with torch.cuda.stream(streams[r]):
+          ops[r].apply_partitioned(us[r], ys[r], plans[r],
+                                   blks[r].num_interface_elements, lam=lam,
+                                   mu=mu, dot_out=dots[r])
+    else:
+      # every rank's apply + push first (a push never waits), then the waits
+      for r in range(world):
+        ops[r].apply_partitioned(us[r], ys[r], plans[r],
+                                 blks[r].num_interface_elements, lam=lam,
+                                 mu=mu, dot_out=dots[r], wait=False)
+      for r in range(world):
+        plans[r].p2p_wait_unpack(ys[r])
     torch.cuda.synchronize()
     total_dot = 0.0
     for r in range(world):
