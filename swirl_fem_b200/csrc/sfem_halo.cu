@@ -513,14 +513,24 @@ int sfem_halo_wait_unpack(sfem_halo* halo, void* u, sfem_stream_t stream_) {
   // spins on counters the apply advances), one CTA per SM so that it fits the
   // spare warp slots; never without the programmatic-dependent attribute
   const int early = halo->fuse_unpack >= 2 && halo->last_push_fused && wait_pdl;
-  if (early && b > num_sms()) b = num_sms();
+  // concurrent mode: 64-thread CTAs, so that they fit next to the apply's
+  // resident CTAs (5 x 64 threads x 168 registers leave ~11 k registers per
+  // SM: a 256-thread CTA would only start once apply CTAs exit -- measured:
+  // flags raised AFTER the apply's exit), four per SM
+  const int threads = early ? 64 : kThreads;
+  if (early) {
+    b = hd.num_uslices > hd.num_slices ? hd.num_uslices : hd.num_slices;
+    const int64_t ecap = wait_ctas > 0 ? wait_ctas : (int64_t)num_sms() * 4;
+    if (b > ecap) b = ecap;
+    if (b < 1) b = 1;
+  }
   if (d.dtype == SFEM_F64)
     SFEM_CUDA_CHECK(launch_maybe_pdl(wait_pdl, halo_wait_unpack_kernel<double>,
-                                     dim3((unsigned)b), dim3(kThreads), 0,
+                                     dim3((unsigned)b), dim3(threads), 0,
                                      stream, (double*)u, hd, early));
   else
     SFEM_CUDA_CHECK(launch_maybe_pdl(wait_pdl, halo_wait_unpack_kernel<float>,
-                                     dim3((unsigned)b), dim3(kThreads), 0,
+                                     dim3((unsigned)b), dim3(threads), 0,
                                      stream, (float*)u, hd, early));
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;

@@ -8,7 +8,7 @@ timeout 600 python -m pytest tests -m gpu -q -p no:cacheprovider --tb=short -k "
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 B="bench.py --gpus 2 --ne 42 --steps 40 --warmup 5 --no-e2e --no-parity --cg-iters 40"
 i=0
-for env in "SFEM_HALO_FUSE_UNPACK=2" "SFEM_HALO_FUSE_UNPACK=3" "SFEM_HALO_FUSE_UNPACK=3 SFEM_WAIT_CTAS=296" "SFEM_HALO_FUSE_UNPACK=1"; do
+for env in "SFEM_HALO_FUSE_UNPACK=2" "SFEM_HALO_FUSE_UNPACK=3" "SFEM_HALO_FUSE_UNPACK=3 SFEM_WAIT_CTAS=148" "SFEM_HALO_FUSE_UNPACK=3 SFEM_WAIT_CTAS=1184"; do
   i=$((i+1))
   env $env timeout 600 $TR --master-port $((29530+i)) $B > $O/r2_n2_ne42_$i.json 2> $O/r2_n2_ne42_$i.err
   python - "$O/r2_n2_ne42_$i.json" "$env" <<'PY'
