@@ -30,7 +30,7 @@ struct sfem_halo {
   unsigned cur_uslice = 256; // canonical-sum work-item size of this epoch
   unsigned cur_slice = 256;  // push work-item size of this epoch
   unsigned cur_grid = 0;     // CTAs of this epoch's fused apply
-  int fuse_unpack = 1;
+  int fuse_unpack = 3;  // see sfem_halo_set_option key 1
   bool last_push_fused = false;  // the current epoch's push ran inside an apply
 };
 
