@@ -300,8 +300,19 @@ int sfem_halo_create(const sfem_halo_desc* desc, sfem_halo** halo);
 void sfem_halo_destroy(sfem_halo* halo);
 
 /* Tuning (call between epochs only).  key 0: entries per work item of the
- * cooperative push / sum (default 256); key 1: whether the fused apply also
- * runs the canonical sum inside its kernel (default 1). */
+ * cooperative push / sum (default 256); key 1: who runs the exchange of
+ * sfem_op_apply_halo --
+ *   0  push inside the apply kernel, canonical sum in sfem_halo_wait_unpack
+ *      (runs after the apply);
+ *   1  push and canonical sum inside the apply kernel's CTAs;
+ *   2  push inside the apply kernel, canonical sum in the kernel of
+ *      sfem_halo_wait_unpack running CONCURRENTLY with the apply's interior
+ *      elements (programmatic dependent launch, 64-thread CTAs in spare slots);
+ *   3  (default) push AND canonical sum in that concurrent kernel: the apply's
+ *      CTAs only signal the end of their interface elements.
+ * In modes 2 / 3 the exchange progresses only once sfem_halo_wait_unpack has
+ * been enqueued on the apply's stream: call it right after sfem_op_apply_halo
+ * (ranks sharing ONE stream of one device would wait for one another). */
 int sfem_halo_set_option(sfem_halo* halo, int32_t key, int64_t value);
 
 /* Starts a new epoch: u's shared dofs -> the peers' receive buffers, then

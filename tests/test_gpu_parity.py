@@ -884,12 +884,19 @@ def test_fused_distributed_cg_single_process(case):
   # that can block until running kernels finish -- with all ranks in ONE
   # process a rank's wait kernel would then spin against the 4 s limit while
   # the host is stuck loading (one process per GPU never has this problem).
+  # (The warm-up runs all ranks on ONE stream, so the push must happen inside
+  # the apply -- exchange mode 1; in the default mode 3 it happens in the
+  # companion kernel, which here would sit behind the peers' applies.)
   warm = [torch.empty_like(st['rhs']) for st in ranks]
+  for pl in plans:
+    pl.p2p_set_option(1, 1)
   for r, st in enumerate(ranks):
     st['op'].apply_partitioned(st['rhs'], warm[r], plans[r],
                                blks[r].num_interface_elements, wait=False)
   for r in range(world):
     plans[r].p2p_wait_unpack(warm[r])
+  for pl in plans:
+    pl.p2p_set_option(1, 3)
   from swirl_fem_b200.communication.dist_cg import distributed_cg
   distributed_cg(ranks[0]['op'], None, ranks[0]['rhs'], tol=0.0, maxiter=2)
   torch.cuda.synchronize()
