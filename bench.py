@@ -456,6 +456,31 @@ def run_ours(args):
       dist.barrier()
     torch.cuda.synchronize()
 
+  # lazy zero fill (companion kernel): checked against the eager fill on this
+  # very workload before anything is timed; any doubt -> eager
+  zero_fill = 'eager: before the apply'
+  if getattr(op, '_lazy', None) and world == 1:
+    y_lazy = op.apply(x, lam=0.0, mu=1.0).clone()
+    y_lazy2 = op.apply(x, lam=0.0, mu=1.0).clone()   # counters were reset
+    op.disable_lazy_zero()
+    y_eager = op.apply(x, lam=0.0, mu=1.0)
+    scale = float(y_eager.abs().max())
+    diff = max(float((y_lazy - y_eager).abs().max()),
+               float((y_lazy2 - y_eager).abs().max())) / scale
+    del y_lazy, y_lazy2, y_eager
+    msg = None
+    if diff <= (1e-13 if dtype == torch.float64 else 2e-5):
+      op.enable_lazy_zero()
+      op.apply(x, lam=0.0, mu=1.0, out=y)
+      msg = op.lazy_zero_timed_out()
+    if op._lazy and not msg:
+      zero_fill = ('lazy: companion kernel next to the apply '
+                   f'(sfem_op_set_lazy_zero); rel. diff vs eager {diff:.1e}')
+    else:
+      op.disable_lazy_zero()
+      zero_fill += f' (lazy fill rejected: diff {diff:.1e}, {msg})'
+      print('bench: ' + zero_fill, file=sys.stderr)
+
   for _ in range(max(args.warmup, 3)):
     step()
   barrier()
@@ -690,6 +715,10 @@ def run_ours(args):
                 'step_with_exchange': [round(a, 5) for a, _ in per_rank],
                 'local_kernel_without_exchange': [round(b, 5)
                                                   for _, b in per_rank]},
+            'zero_fill': zero_fill + (
+                '' if not (getattr(op, '_lazy', None) and world == 1 and
+                           op.lazy_zero_timed_out())
+                else ' -- A WAIT TIMED OUT DURING THE RUN: numbers invalid'),
             'setup_s': t_setup,
         },
         'clocks': clocks,

@@ -149,6 +149,13 @@ SIGNATURES = {
                                            _c_ptr, _c_i32, _c_ptr]),
     'sfem_op_diag': (ctypes.c_int, [_c_ptr, _c_f64, _c_f64, _c_ptr, _c_ptr]),
     'sfem_op_set_variant': (ctypes.c_int, [_c_ptr, _c_i32]),
+    'sfem_op_num_zero': (ctypes.c_int64, [_c_ptr]),
+    'sfem_op_lazy_zero_query': (ctypes.c_int, [
+        _c_ptr, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+        ctypes.POINTER(ctypes.c_int32)]),
+    'sfem_op_set_lazy_zero': (ctypes.c_int, [_c_ptr, _c_ptr, _c_i64, _c_ptr,
+                                             _c_i32, _c_i32, _c_i64, _c_i32]),
+    'sfem_op_lazy_zero_timed_out': (ctypes.c_int, [_c_ptr, _c_ptr]),
     'sfem_cg_workspace_bytes': (_c_i64, [ctypes.c_int, _c_i64]),
     'sfem_cg': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr,
                                ctypes.POINTER(CgParams), _c_ptr,

@@ -16,6 +16,7 @@ The handle owns two device buffers (torch tensors, caller-visible):
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -76,6 +77,66 @@ class FusedOperator:
     self.handle = handle
     self.num_nodes = mesh.num_nodes
     self.ndim = mesh.ndim
+    self._lazy = None
+    # SFEM_LAZY_ZERO: 0 never, 1 whenever a lazy instance exists, default: when
+    # the shared-dof prefix is larger than half of L2 (the eager fill's zeros
+    # are then evicted before the first accumulation reaches them)
+    mode = os.environ.get('SFEM_LAZY_ZERO', 'auto')
+    if mode != '0' and mesh.ndim == 3 and interp.collocated:
+      nz = int(lib.sfem_op_num_zero(handle))
+      if mode == '1' or nz * esz >= (64 << 20):
+        self.enable_lazy_zero()
+
+  def enable_lazy_zero(self, ahead: float | None = None,
+                       report_every: int | None = None,
+                       piece: int = 1024) -> bool:
+    """Builds the tables of the lazy zero fill (`sfem_op_set_lazy_zero`): a
+    companion kernel then zeroes y's shared dofs while the apply runs, each
+    shortly before its first accumulation (see `lazy_zero_tables`).  `ahead`:
+    how many rounds of CTA steps the companion may run ahead of the apply.
+    Returns False -- the eager fill stays -- when this operator has no lazy
+    kernel instance or the mesh is too small."""
+    lib = _lib.lib()
+    se, grid, sup = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    _lib._check(lib.sfem_op_lazy_zero_query(
+        self.handle, ctypes.byref(se), ctypes.byref(grid), ctypes.byref(sup)),
+                'sfem_op_lazy_zero_query')
+    if not sup.value:
+      return False
+    if ahead is None:
+      ahead = float(os.environ.get('SFEM_LAZY_AHEAD', 4))
+    if report_every is None:
+      report_every = int(os.environ.get('SFEM_LAZY_REPORT', 4))
+    tables = lazy_zero_tables(
+        self.mesh.elements, self.num_nodes,
+        int(lib.sfem_op_num_zero(self.handle)), se.value, grid.value, piece)
+    if tables is None:
+      return False
+    pieces, chunk_ptr = tables
+    ahead_steps = max(int(round(ahead * grid.value)),
+                      report_every * grid.value)
+    with torch.cuda.device(pieces.device):
+      _lib._check(lib.sfem_op_set_lazy_zero(
+          self.handle, _lib.ptr(pieces), int(pieces.shape[0]),
+          _lib.ptr(chunk_ptr), int(chunk_ptr.numel() - 1), grid.value,
+          ahead_steps, report_every), 'sfem_op_set_lazy_zero')
+    self._lazy = (pieces, chunk_ptr)   # the C side retains these pointers
+    return True
+
+  def disable_lazy_zero(self):
+    _lib._check(_lib.lib().sfem_op_set_lazy_zero(
+        self.handle, None, 0, None, 0, 0, 0, 1), 'sfem_op_set_lazy_zero')
+    self._lazy = None
+
+  def lazy_zero_timed_out(self) -> str:
+    """'' or the record of the first device-side wait that hit its limit
+    (every result since then is invalid).  Synchronises."""
+    dev = self.geom.device
+    lib = _lib.lib()
+    with torch.cuda.device(dev):
+      if lib.sfem_op_lazy_zero_timed_out(self.handle, _lib.stream_ptr(dev)):
+        return lib.sfem_last_error().decode()
+    return ''
 
   def __del__(self):
     h = getattr(self, 'handle', None)
@@ -215,6 +276,68 @@ class FusedOperator:
   def bind(self, lam: float = 0.0, mu: float = 1.0):
     """Returns the callable `A(u)` for these coefficients (for `linalg.cg`)."""
     return BoundOperator(self, lam, mu)
+
+
+def lazy_zero_tables(elements: torch.Tensor, num_nodes: int, num_zero: int,
+                     step_elems: int, grid: int, piece: int = 2048):
+  """Tables of the lazy zero fill (see `sfem_op_set_lazy_zero`).
+
+  The apply's persistent CTAs run their j-th step at about the same time (CTA b
+  processes steps b, b + grid, ...), so the elements are cut into chunks of
+  `grid` steps = `grid * step_elems` elements; every dof of the shared prefix
+  [0, num_zero) belongs to the chunk that touches it FIRST (dofs no element
+  touches: chunk 0).  Returns `(pieces int32 (P, 2) = {first dof, length |
+  chunk << 12}, chunk_ptr int32 (num_chunks + 1,))` -- pieces sorted by chunk, never
+  crossing a chunk boundary or a gap in the ids, at most `piece` dofs long --
+  or None when there are fewer than 4 chunks.  Index arithmetic only (torch,
+  any device; set-up time)."""
+  E, n = int(elements.shape[0]), int(elements.shape[1])
+  if (step_elems <= 0 or grid <= 0 or num_zero <= 0 or num_nodes >= 2 ** 31
+      or not 1 <= piece <= 4095):
+    return None
+  chunk_elems = grid * step_elems
+  num_chunks = -(-E // chunk_elems)
+  if num_chunks < 4 or num_chunks >= (1 << 19):
+    return None
+  dev = elements.device
+  big = torch.iinfo(torch.int32).max
+  nz = int(num_zero)
+  first = torch.full((nz,), big, dtype=torch.int64, device=dev)
+  # element blocks keep the temporaries small on 10^8-dof meshes
+  blk = max(1, (1 << 26) // max(n, 1))
+  for e0 in range(0, E, blk):
+    ids = elements[e0:e0 + blk].reshape(-1).long()
+    chunk = (torch.arange(e0, min(e0 + blk, E), device=dev)
+             // chunk_elems).repeat_interleave(n)
+    sel = (ids >= 0) & (ids < nz)
+    first.scatter_reduce_(0, ids[sel], chunk[sel], 'amin', include_self=True)
+    del ids, chunk, sel
+  first = torch.where(first == big, torch.zeros_like(first), first)
+  order = torch.argsort(first, stable=True)            # ids by chunk, then id
+  st = first[order]
+  # position in `order` of the first dof of chunk c, c = 0 .. num_chunks
+  bounds = torch.searchsorted(
+      st, torch.arange(0, num_chunks + 1, device=dev, dtype=st.dtype))
+  cut = torch.zeros(nz + 1, dtype=torch.bool, device=dev)
+  cut[0] = True
+  cut[1:nz] = order[1:] != order[:-1] + 1               # gaps in the ids
+  cut[bounds.clamp(max=nz)] = True                      # chunk boundaries
+  seg_start = torch.nonzero(cut[:nz]).reshape(-1)
+  seg_end = torch.cat([seg_start[1:], torch.tensor([nz], device=dev)])
+  npieces = (seg_end - seg_start + piece - 1) // piece
+  seg_of_piece = torch.repeat_interleave(
+      torch.arange(seg_start.numel(), device=dev), npieces)
+  first_piece = torch.cumsum(npieces, 0) - npieces
+  k = torch.arange(seg_of_piece.numel(), device=dev) - first_piece[seg_of_piece]
+  pos = seg_start[seg_of_piece] + k * piece
+  plen = torch.minimum(torch.full_like(pos, piece),
+                       seg_end[seg_of_piece] - pos)
+  pchunk = st[pos]
+  pieces = torch.stack([order[pos], plen + (pchunk << 12)],
+                       dim=1).to(torch.int32).contiguous()
+  # first piece of chunk c = number of pieces starting before its first dof
+  chunk_ptr = torch.searchsorted(pos, bounds).to(torch.int32).contiguous()
+  return pieces, chunk_ptr
 
 
 class HostPipeline:

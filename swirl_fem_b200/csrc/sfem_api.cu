@@ -134,9 +134,27 @@ bool pdl_enabled() {
 // shared by sfem_op_apply and the CG driver
 // `prezeroed`: y[0 .. n_zero) and *dot_xy are already zero (fused CG loop: the
 // previous cg_step_kernel did it), so no fill is enqueued.
+// True when this launch zero-fills lazily (tables set, supported launch, and
+// the operator's lazy launches all on ONE stream: the counters are per handle).
+bool lazy_zero_applicable(const sfem_op* op, int ncomp, cudaStream_t stream) {
+  const sfem_space_desc& d = op->base.desc;
+  if (op->lazy_chunk_ptr == nullptr || ncomp != 1 || op->variant != 0 ||
+      !d.collocated || d.dim != 3 || op->fuse != nullptr)
+    return false;
+  LazyHost* h = op->lazy_host;
+  if (h == nullptr) return false;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!h->has_stream) {
+    h->stream = stream;
+    h->has_stream = true;
+  }
+  return h->stream == stream;
+}
+
 int op_apply_internal(const sfem_op* op, double lambda, double mu,
                       const void* x, void* y, int ncomp, double* dot_xy,
-                      cudaStream_t stream, bool prezeroed = false) {
+                      cudaStream_t stream, bool prezeroed = false,
+                      bool dot_prezeroed = false) {
   const sfem_space_desc& d = op->base.desc;
   SFEM_REQUIRE(lambda == 0.0 || op->with_mass,
                "operator was created without mass factors (with_mass = 0) but "
@@ -154,6 +172,14 @@ int op_apply_internal(const sfem_op* op, double lambda, double mu,
   sfem_op sub = *op;
   if (prezeroed) {
     sub.pdl = false;
+  } else if (lazy_zero_applicable(op, ncomp, stream)) {
+    // the companion kernel zeroes y's prefix while the apply runs.  (Not the
+    // dot accumulator: nothing orders the companion's first instruction
+    // before the apply's last.)
+    sub.pdl = false;
+    sub.lazy = true;
+    if (dot_xy && !dot_prezeroed)
+      SFEM_CUDA_CHECK(cudaMemsetAsync(dot_xy, 0, sizeof(double), stream));
   } else if (pdl) {
     int rc = launch_zero_fill(y, esz * (size_t)op->n_zero * ncomp, dot_xy,
                               stream, &sub.pdl);
@@ -320,8 +346,115 @@ int sfem_op_create(const sfem_space_desc* desc, const uint8_t* dirichlet,
 
 void sfem_op_destroy(sfem_op* op) {
   if (!op) return;
+  if (op->lazy_counters) cudaFree(op->lazy_counters);
+  delete op->lazy_host;
   sfem::space_base_free(&op->base);
   delete op;
+}
+
+int64_t sfem_op_num_zero(const sfem_op* op) { return op ? op->n_zero : -1; }
+
+int sfem_op_lazy_zero_query(const sfem_op* op, int32_t* step_elems,
+                            int32_t* grid, int32_t* supported) {
+  using namespace sfem;
+  SFEM_REQUIRE(op && step_elems && grid && supported, "null argument");
+  const sfem_space_desc& d = op->base.desc;
+  *step_elems = *grid = *supported = 0;
+  if (!d.collocated || d.dim != 3 || d.n1d > 16 || d.num_elements <= 0 ||
+      op->variant != 0)
+    return SFEM_OK;
+  unsigned q[3] = {0, 0, 0};
+  sfem_op sub = *op;
+  sub.query = q;
+  sub.fuse = nullptr;
+  sub.lazy = false;
+  // (nothing is launched: the launcher returns after sizing its grid)
+  const int rc =
+      d.dtype == SFEM_F64
+          ? apply_dispatch<double>(sub, 0.0, 1.0, op->conn, op->conn, 1, false,
+                                   nullptr, nullptr)
+          : apply_dispatch<float>(sub, 0.0, 1.0, op->conn, op->conn, 1, false,
+                                  nullptr, nullptr);
+  if (rc) return rc;
+  *step_elems = (int32_t)q[0];
+  *grid = (int32_t)q[1];
+  *supported = (int32_t)q[2];
+  return SFEM_OK;
+}
+
+int sfem_op_set_lazy_zero(sfem_op* op, const void* pieces, int64_t num_pieces,
+                          const void* chunk_ptr, int32_t num_chunks,
+                          int32_t grid, int64_t ahead_steps,
+                          int32_t report_every) {
+  using namespace sfem;
+  SFEM_REQUIRE(op != nullptr, "null argument");
+  if (chunk_ptr == nullptr) {  // back to the eager fill
+    op->lazy_pieces = nullptr;
+    op->lazy_chunk_ptr = nullptr;
+    op->lazy_num_chunks = 0;
+    return SFEM_OK;
+  }
+  SFEM_REQUIRE(pieces && num_pieces >= 0 && num_pieces < (1ll << 31) &&
+                   num_chunks >= 2 && grid > 0,
+               "bad lazy zero tables");
+  SFEM_REQUIRE(report_every == 1 || report_every == 2 || report_every == 4 ||
+                   report_every == 8,
+               "report_every must be 1, 2, 4 or 8");
+  // the progress counter moves in units of report_every steps per CTA: the
+  // pacing window must cover that, or the last chunks would never be released
+  SFEM_REQUIRE(ahead_steps >= (int64_t)report_every * grid &&
+                   ahead_steps < (1ll << 31),
+               "ahead_steps must be at least report_every * grid");
+  int32_t se = 0, g = 0, sup = 0;
+  int rc = sfem_op_lazy_zero_query(op, &se, &g, &sup);
+  if (rc) return rc;
+  SFEM_REQUIRE(sup == 1 && g == grid,
+               "lazy zero fill: not supported for this operator, or the tables "
+               "were built for another grid");
+  if (op->lazy_counters) {
+    SFEM_CUDA_CHECK(cudaDeviceSynchronize());
+    SFEM_CUDA_CHECK(cudaFree(op->lazy_counters));
+    op->lazy_counters = nullptr;
+  }
+  // + 8 words: record of the first wait that timed out (debugging)
+  // and the work-queue head + done-CTA count of the companion kernel
+  const size_t bytes = ((size_t)num_chunks + 2 + 8 + 2) * sizeof(unsigned);
+  SFEM_CUDA_CHECK(cudaMalloc(&op->lazy_counters, bytes));
+  SFEM_CUDA_CHECK(cudaMemset(op->lazy_counters, 0, bytes));
+  SFEM_CUDA_CHECK(cudaDeviceSynchronize());
+  if (!op->lazy_host) op->lazy_host = new LazyHost();
+  op->lazy_host->has_stream = false;
+  op->lazy_pieces = (const int2*)pieces;
+  op->lazy_chunk_ptr = (const int32_t*)chunk_ptr;
+  op->lazy_num_chunks = num_chunks;
+  op->lazy_num_pieces = (int)num_pieces;
+  op->lazy_grid = (unsigned)grid;
+  op->lazy_ahead = (unsigned)ahead_steps;
+  op->lazy_report_mask = (unsigned)report_every - 1u;
+  return SFEM_OK;
+}
+
+int sfem_op_lazy_zero_timed_out(const sfem_op* op, sfem_stream_t stream) {
+  if (!op || !op->lazy_counters) return 0;
+  unsigned v = 0, dbg[5] = {0, 0, 0, 0, 0};
+  if (cudaMemcpyAsync(&v, op->lazy_counters + 1, sizeof(v),
+                      cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess)
+    return 1;
+  if (cudaMemcpyAsync(dbg, op->lazy_counters + 2 + op->lazy_num_chunks,
+                      sizeof(dbg), cudaMemcpyDeviceToHost,
+                      (cudaStream_t)stream) != cudaSuccess)
+    return 1;
+  if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return 1;
+  if (v != 0) {
+    char msg[256];
+    snprintf(msg, sizeof(msg),
+             "lazy zero fill: first timeout in %s %u at chunk %u (saw %u, "
+             "progress counter %u; grid %u, chunks %d)",
+             dbg[0] == 1 ? "apply CTA" : "companion warp", dbg[1], dbg[2],
+             dbg[3], dbg[4], op->lazy_grid, op->lazy_num_chunks);
+    sfem::set_error(msg);
+  }
+  return v != 0;
 }
 
 int sfem_op_set_variant(sfem_op* op, int32_t variant) {

@@ -245,8 +245,12 @@ __device__ __forceinline__ void bulk_copy_g2s_evict_first(void* smem_dst,
 //          of the next element's connectivity, a DRAM load issued only one
 //          barrier earlier);
 //   EVICT: factors staged with the evict-first copy above.
+//   LAZY:  y's shared-dof prefix is zeroed by the companion lazy_zero_kernel
+//          while this kernel runs (LazyDev in sfem_common.cuh): a step scatters
+//          only once its chunk's counter is complete.
 template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH,
-          bool HALO = false, bool CONN2 = false, bool EVICT = false>
+          bool HALO = false, bool CONN2 = false, bool EVICT = false,
+          bool LAZY = false>
 __global__ void __launch_bounds__((Cfg3DV2<T, N, EPB, MINB, KCH>::threads),
                                   MINB)
 apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
@@ -254,7 +258,9 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
                   const T* __restrict__ gf, T lambda, T mu,
                   const T* __restrict__ x, T* __restrict__ y, int ncomp,
                   int64_t E, double* __restrict__ dot_xy,
-                  const __grid_constant__ HaloDev hd) {
+                  const __grid_constant__ HaloDev hd,
+                  const __grid_constant__ LazyDev lz) {
+  static_assert(!LAZY || (!HALO && !LOCAL), "lazy zero fill: global form only");
   using C = Cfg3DV2<T, N, EPB, MINB, KCH>;
   constexpr int P = C::P, n = C::n, epb = C::epb;
   constexpr int S0 = C::S0, R = C::R;
@@ -380,10 +386,19 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       nrc_c[k] = a1 ? ld_stream(conn + e1 * n + k * P + t) : kConnSentinel;
   }
 
+  // LAZY: this CTA's step number is its chunk index
+  __shared__ unsigned s_lz;
+  unsigned lz_it = 0, lz_seen = 0, lz_need = 0;
+
   int buf = 0;
   for (; blk < nblocks; blk += gridDim.x, buf ^= 1) {
     T* sU = sU0 + buf * C::tile;
     T* sUn = sU0 + (buf ^ 1) * C::tile;
+    if (LAZY && threadIdx.x == 0) {
+      lz_seen = ld_relaxed_gpu(&lz.counters[2 + lz_it]);
+      lz_need = (unsigned)(__ldg(lz.chunk_ptr + lz_it + 1) -
+                           __ldg(lz.chunk_ptr + lz_it));
+    }
     // ---- pipeline: next element's factors -> L2, connectivity -> registers
     const int64_t blk_n = blk + gridDim.x;
     const int64_t e_n = blk_n * epb + slot;
@@ -588,6 +603,7 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
         for (int k = 0; k < N; ++k) ry[k] += ucol[k];
       }
     }
+    if (LAZY && threadIdx.x == 0) s_lz = lz_seen >= lz_need;
     __syncthreads();
     if (STAGE) {
       // every thread of the slot is done reading the staged factors: refill
@@ -614,7 +630,28 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     __syncthreads();
 
     // ---- phase 5 (mapping A): sum the three parts, scatter
-    if (first_step) {
+    if (LAZY) {
+      // (s_lz was written before the barrier after phase 3 and is not written
+      // again before the next step's barriers.)  The relaxed poll suffices on
+      // the fast path: the zeros were fenced before the count, and the REDs
+      // below are L2 operations issued after the count was seen.
+      if (!s_lz) {
+        if (threadIdx.x == 0 && ld_relaxed_gpu(&lz.counters[1]) == 0 &&
+            !spin_u32_relaxed_ge(&lz.counters[2 + lz_it], lz_need, 250,
+                                 2000000000ull)) {
+          // sticky: later steps do not wait again.  First failure: who / what
+          unsigned* dbg = lz.counters + 2 + lz.num_chunks;
+          if (atomicCAS(dbg, 0u, 1u) == 0u) {
+            dbg[1] = blockIdx.x;
+            dbg[2] = lz_it;
+            dbg[3] = ld_relaxed_gpu(&lz.counters[2 + lz_it]);
+            dbg[4] = ld_relaxed_gpu(&lz.counters[0]);
+          }
+          lz.counters[1] = 1u;
+        }
+        __syncthreads();
+      }
+    } else if (first_step) {
       pdl_wait();
       first_step = false;
     }
@@ -650,6 +687,12 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
 #pragma unroll
     for (int k = 0; k < N; ++k) rc[k] = nrc[k];
     if (HALO && hstate == kHIface && blk_n >= hd.n_if_blocks) __threadfence();
+    if (LAZY) {
+      // progress report (a hint for the companion's pacing: no ordering needed)
+      ++lz_it;
+      if (threadIdx.x == 0 && (lz_it & lz.report_mask) == 0)
+        red_add_u32(&lz.counters[0], lz.report_mask + 1u);
+    }
   }
   cp_async_wait_all();
   if (HALO) {
@@ -700,8 +743,89 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
   }
 }
 
+// Companion of a LAZY apply (LazyDev in sfem_common.cuh): zeroes piece after
+// piece of y's shared-dof prefix in first-touch order, paced by the apply's
+// progress counter.  The pieces are a work queue (one warp claims one piece at
+// a time), so it does not matter how many of this kernel's CTAs find room next
+// to the apply's: one resident warp is enough for progress.  Every lane fences
+// its own stores, lane 0 fences again after the warp has converged and counts
+// the piece on its chunk.  Launched as the apply's programmatic dependent so
+// that it runs NEXT to it; it waits for the primary only once its work is done.
+template <typename T>
+__global__ void __launch_bounds__(64)
+lazy_zero_kernel(T* __restrict__ y, const LazyDev lz) {
+  constexpr int VW = 16 / (int)sizeof(T);
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned* head = lz.counters + 2 + lz.num_chunks + 8;
+  bool dead = false;
+  for (;;) {
+    int p = 0;
+    if (lane == 0) p = (int)atomicAdd(head, 1u);
+    p = __shfl_sync(0xffffffffu, p, 0);
+    if (p >= lz.num_pieces) break;
+    const int2 pc = __ldg(lz.pieces + p);
+    const unsigned j = (unsigned)pc.y >> 12;
+    const uint64_t need = (uint64_t)j * lz.grid;
+    if (need > lz.ahead && !dead) {
+      int ok = 1;
+      if (lane == 0)
+        ok = spin_u32_relaxed_ge(&lz.counters[0], (unsigned)(need - lz.ahead),
+                                 1000, 2000000000ull);
+      ok = __shfl_sync(0xffffffffu, ok, 0);
+      if (!ok) {
+        dead = true;  // the apply made no progress: zero the rest unpaced
+        if (lane == 0) {
+          unsigned* dbg = lz.counters + 2 + lz.num_chunks;
+          if (atomicCAS(dbg, 0u, 2u) == 0u) {
+            dbg[1] = blockIdx.x;
+            dbg[2] = j;
+            dbg[3] = (unsigned)(need - lz.ahead);
+            dbg[4] = ld_relaxed_gpu(&lz.counters[0]);
+          }
+          lz.counters[1] = 1u;
+        }
+      }
+    }
+    T* d = y + pc.x;
+    int len = pc.y & 0xfff;
+    int hd = (int)(((16u - (unsigned)((uintptr_t)d & 15u)) & 15u) / sizeof(T));
+    hd = hd < len ? hd : len;
+    if ((int)lane < hd) d[lane] = T(0);
+    d += hd;
+    len -= hd;
+    const int nv = len / VW;
+    float4* d4 = reinterpret_cast<float4*>(d);
+    for (int i = lane; i < nv; i += 32) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int tail = nv * VW + (int)lane;
+    if (tail < len) d[tail] = T(0);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      red_add_u32(&lz.counters[2 + j], 1u);
+    }
+  }
+  // The apply has consumed every counter once it has completed; the LAST CTA
+  // of this kernel to get here resets them (the others may still be claiming).
+  pdl_wait();
+  __shared__ unsigned s_last;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    s_last = atomicAdd(head + 1, 1u) + 1u == gridDim.x;
+  __syncthreads();
+  if (s_last) {
+    for (int i = threadIdx.x; i < lz.num_chunks + 2; i += blockDim.x)
+      if (i != 1) lz.counters[i] = 0u;
+    if (threadIdx.x == 0) {
+      head[0] = 0u;
+      head[1] = 0u;
+    }
+  }
+}
+
 template <typename T, int N, bool MASS, bool LOCAL, int EPB, int MINB, int KCH,
-          bool HALO = false, bool CONN2 = false, bool EVICT = false>
+          bool HALO = false, bool CONN2 = false, bool EVICT = false,
+          bool LAZY = false>
 int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
                     void* y, int ncomp, double* dot_xy, cudaStream_t stream) {
   using C = Cfg3DV2<T, N, EPB, MINB, KCH>;
@@ -711,8 +835,8 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
       ((size_t)C::stage_off(C::epb) +
        (KCH == 0 ? (size_t)C::epb * (MASS ? 7 : 6) * C::n : 0)) *
       sizeof(T);
-  auto kernel =
-      apply3d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB, KCH, HALO, CONN2, EVICT>;
+  auto kernel = apply3d_v2_kernel<T, N, MASS, LOCAL, EPB, MINB, KCH, HALO, CONN2,
+                                  EVICT, LAZY>;
   static int per_sm_dev[64] = {};
   int& per_sm = per_device_slot(per_sm_dev);
   if (per_sm == 0) {
@@ -731,6 +855,45 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
   const int64_t steps_per_cta = (nblocks + cap - 1) / cap;
   const int64_t even = (nblocks + steps_per_cta - 1) / steps_per_cta;
   dim3 grid((unsigned)(nblocks < cap ? nblocks : even), ncomp);
+  if (op.query) {  // table set-up: report the launch geometry only
+    op.query[0] = (unsigned)C::epb;
+    op.query[1] = grid.x;
+    return SFEM_OK;
+  }
+  LazyDev lz{};
+  unsigned lazy_ctas = 0;
+  if (LAZY) {
+    if (op.lazy_grid != grid.x || ncomp != 1 || op.lazy_counters == nullptr) {
+      set_error("lazy zero fill: tables were built for another launch geometry");
+      return SFEM_ERR_INVALID;
+    }
+    // Load the companion BEFORE the apply is enqueued: CUDA loads a kernel at
+    // its first launch, and that load can block until running kernels finish
+    // -- the apply's CTAs would sit in their bounded wait for a companion
+    // that cannot be launched.
+    static int loaded_dev[64] = {};
+    int& loaded = per_device_slot(loaded_dev);
+    if (!loaded) {
+      cudaFuncAttributes fa;
+      SFEM_CUDA_CHECK(cudaFuncGetAttributes(&fa, lazy_zero_kernel<T>));
+      SFEM_CUDA_CHECK(cudaFuncGetAttributes(&fa, kernel));
+      loaded = 1;
+    }
+    static int lazy_ctas_env = -1;
+    if (lazy_ctas_env < 0) {
+      const char* e = getenv("SFEM_LAZY_CTAS");
+      lazy_ctas_env = e ? atoi(e) : 0;
+    }
+    lazy_ctas = lazy_ctas_env > 0 ? (unsigned)lazy_ctas_env : (unsigned)num_sms();
+    lz.pieces = op.lazy_pieces;
+    lz.chunk_ptr = op.lazy_chunk_ptr;
+    lz.counters = op.lazy_counters;
+    lz.num_chunks = op.lazy_num_chunks;
+    lz.grid = grid.x;
+    lz.ahead = op.lazy_ahead;
+    lz.report_mask = op.lazy_report_mask;
+    lz.num_pieces = op.lazy_num_pieces;
+  }
   DOps<T, N> dm;
   fill_even_odd<T, N>(op.base.h_BD, false, &dm.fwd);
   fill_even_odd<T, N>(op.base.h_BD, true, &dm.bwd);
@@ -759,8 +922,13 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
   SFEM_CUDA_CHECK(launch_maybe_pdl(
       op.pdl, kernel, grid, dim3(C::threads), smem, stream, dm, op.conn,
       (const T*)op.geom, (T)lambda, (T)mu, (const T*)x, (T*)y, ncomp, E,
-      dot_xy, hd));
+      dot_xy, hd, lz));
   SFEM_LAUNCH_CHECK();
+  if (LAZY) {
+    SFEM_CUDA_CHECK(launch_maybe_pdl(true, lazy_zero_kernel<T>, dim3(lazy_ctas),
+                                     dim3(64), 0, stream, (T*)y, lz));
+    SFEM_LAUNCH_CHECK();
+  }
   return SFEM_OK;
 }
 
@@ -796,18 +964,19 @@ struct AutoCfg3D {
 // at N = 8 fp64 (81 % -> 89 % of the HBM roofline at 108 M dofs), +8 % at
 // N = 6 fp64, +1.5 % at N = 8 fp32, and cost 1-4 % for the other measured
 // (precision, N) -- those keep the one-step / default-policy pipeline.
+// `lazy`: a LAZY instance (zero fill by the companion kernel) is compiled.
 template <typename T, int N>
 struct Tune3D {
-  static constexpr bool conn2 = false, evict = false;
+  static constexpr bool conn2 = false, evict = false, lazy = false;
 };
 template <> struct Tune3D<double, 6> {
-  static constexpr bool conn2 = true, evict = true;
+  static constexpr bool conn2 = true, evict = true, lazy = false;
 };
 template <> struct Tune3D<double, 8> {
-  static constexpr bool conn2 = true, evict = true;
+  static constexpr bool conn2 = true, evict = true, lazy = true;
 };
 template <> struct Tune3D<float, 8> {
-  static constexpr bool conn2 = true, evict = true;
+  static constexpr bool conn2 = true, evict = true, lazy = true;
 };
 
 constexpr int clamp_int(int v, int lo, int hi) {
@@ -893,6 +1062,13 @@ int launch3d_v2(const sfem_op& op, double lambda, double mu, const void* x,
   }
 #endif
   using Tn = Tune3D<T, N>;
+  if constexpr (Tn::lazy && !LOCAL) {
+    if (op.query) op.query[2] = 1u;  // a LAZY instance exists
+    if (op.lazy)
+      return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
+                             Tn::conn2, Tn::evict, true>(
+          op, lambda, mu, x, y, ncomp, dot_xy, stream);
+  }
   return launch3d_v2_cfg<T, N, MASS, LOCAL, EPB, A::MINB, A::KCH, false,
                          Tn::conn2 && !LOCAL, Tn::evict>(
       op, lambda, mu, x, y, ncomp, dot_xy, stream);

@@ -25,7 +25,9 @@ namespace sfem {
 
 int op_apply_internal(const sfem_op* op, double lambda, double mu,
                       const void* x, void* y, int ncomp, double* dot_xy,
-                      cudaStream_t stream, bool prezeroed = false);
+                      cudaStream_t stream, bool prezeroed = false,
+                      bool dot_prezeroed = false);
+bool lazy_zero_applicable(const sfem_op* op, int ncomp, cudaStream_t stream);
 int op_apply_halo_internal(const sfem_op* op, sfem_halo* halo, double lambda,
                            double mu, const void* x, void* y,
                            int64_t num_interface_elements, double* dot_xy,
@@ -433,7 +435,10 @@ int cg_iterate_impl(const sfem_op* op, sfem_halo* halo,
                     void* p, void* Ap, const void* minv, const uint8_t* owned,
                     CgState* st, int iters, cudaStream_t stream) {
   const int64_t n = op->base.desc.num_nodes * (int64_t)ncomp;
-  const int64_t n_zero = op->n_zero * (int64_t)ncomp;
+  // lazy zero fill: the apply's companion kernel zeroes Ap's prefix while the
+  // apply runs, so the step kernel does not
+  const bool lazy = !halo && lazy_zero_applicable(op, ncomp, stream);
+  const int64_t n_zero = lazy ? 0 : op->n_zero * (int64_t)ncomp;
   for (int it = 0; it < iters; ++it) {
     int rc;
     if (halo) {
@@ -442,8 +447,9 @@ int cg_iterate_impl(const sfem_op* op, sfem_halo* halo,
                                   stream);
       if (!rc) rc = sfem_halo_wait_unpack(halo, Ap, (sfem_stream_t)stream);
     } else {
+      // (every step kernel resets p.Ap for the next apply)
       rc = op_apply_internal(op, lambda, mu, p, Ap, ncomp, &st->pAp, stream,
-                             it > 0);
+                             it > 0 && !lazy, it > 0);
     }
     if (rc) return rc;
     rc = launch_cg_step<T>(n, x, r, p, Ap, minv, owned, st, sx, n_zero, stream);

@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <mutex>
 #include <string>
 
 #include "../../include/swirl_b200.h"
@@ -398,6 +399,103 @@ __device__ __forceinline__ bool scalar_allreduce_warp(const ScalarDev& sx,
   return ok;
 }
 
+// ---- lazy zero fill of y's shared-dof prefix (3-D fused apply) ------------------
+// The shared dofs of y are accumulated with RED, so they must be zero first.
+// Filling the whole prefix before the launch costs three DRAM accesses per
+// shared dof instead of one: the zeros are written, evicted (the prefix is
+// 320 MB at 108 M dofs, L2 is 126 MB), fetched again by the first RED and
+// written back.  Lazily, a dof is zeroed shortly before the first element
+// that touches it is scattered, so the line is still in L2 when the REDs
+// arrive and goes to DRAM once.
+//
+// Who zeroes: a COMPANION kernel (lazy_zero_kernel, 64-thread CTAs in the warp
+// slots the apply leaves free, launched as the apply's programmatic dependent
+// so that it runs next to it) -- not the apply's own CTAs: four in-kernel
+// variants reached 0.998 x the algorithmic DRAM traffic but ran 15-45 % slower
+// (fences in the element CTAs, CTAs coupled to one another).
+// The apply's persistent CTAs all execute their j-th step at about the same
+// time (CTA b runs steps b, b + G, b + 2G, ...), so the unit is "chunk j" =
+// the dofs first touched by steps [jG, (j+1)G).  Tables (host-built,
+// sfem_op_set_lazy_zero): `pieces` = {first dof, len | chunk << 12}, sorted by
+// chunk, a work queue for the companion's warps; `chunk_ptr[j]` = first piece
+// of chunk j (dofs no element touches are zeroed with chunk 0).  Protocol on
+// `counters`:
+//   [0]      steps completed by the apply's CTAs (fire-and-forget RED per step);
+//            a piece of chunk j is zeroed once [0] + ahead >= j * G, i.e. a few
+//            steps before it is needed, never further ahead
+//   [1]      sticky: a wait timed out (the result is invalid)
+//   [2 + j]  pieces of chunk j that are zeroed (the warp fences, then counts);
+//            a CTA scatters its step j only after [2 + j] == the number of
+//            pieces of chunk j (relaxed poll issued at the top of the step,
+//            looked at before phase 5)
+//   [2 + num_chunks ..]  8 words: record of the first timed-out wait; then the
+//            queue head and the count of companion CTAs that are done
+// The apply's CTAs never fence, never zero and never wait for one another;
+// the last companion CTA resets the counters after the apply has completed.
+// All polls are RELAXED loads (served by L2, no L1 invalidation on SMs that
+// also run the apply); the consumers of the published zeros are REDs, i.e. L2
+// operations issued after the count was seen.
+struct LazyDev {
+  const int2* pieces;
+  const int32_t* chunk_ptr;  // (num_chunks + 1)
+  unsigned* counters;        // 2 + num_chunks words
+  int num_chunks;
+  unsigned grid;             // G: the apply's grid (CTA steps per chunk)
+  unsigned ahead;            // in CTA steps, see [0]
+  unsigned report_mask;      // a CTA reports every (mask + 1)-th step
+  int num_pieces;
+};
+
+struct LazyHost {
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  bool has_stream = false;
+};
+
+// Bounded wait (~`limit_ns` of globaltimer) for *p >= want; false on a timeout.
+__device__ __forceinline__ bool spin_u32_ge(const unsigned* p, unsigned want,
+                                            unsigned sleep_ns,
+                                            uint64_t limit_ns) {
+  uint64_t t0 = 0;
+  unsigned spins = 0;
+  while (ld_acquire_gpu(p) < want) {
+    __nanosleep(sleep_ns);
+    if ((++spins & 1023u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > limit_ns) return false;
+    }
+  }
+  return true;
+}
+
+// The same with relaxed loads (no L1 invalidation per poll: the pollers share
+// their SMs with the apply's CTAs).  For hints, and for waits whose consumers
+// only issue L2 operations (RED) on the published data afterwards.
+__device__ __forceinline__ bool spin_u32_relaxed_ge(const unsigned* p,
+                                                    unsigned want,
+                                                    unsigned sleep_ns,
+                                                    uint64_t limit_ns) {
+  uint64_t t0 = 0;
+  unsigned spins = 0;
+  while (ld_relaxed_gpu(p) < want) {
+    __nanosleep(sleep_ns);
+    if ((++spins & 255u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > limit_ns) return false;
+    }
+  }
+  return true;
+}
+
+__device__ __forceinline__ void red_add_u32(unsigned* addr, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v)
+               : "memory");
+}
+
 // symmetric index of (i,k), i<=k, in the packed d(d+1)/2 layout
 __host__ __device__ constexpr int sym_index(int dim, int i, int k) {
   return dim == 1 ? 0
@@ -462,6 +560,20 @@ struct sfem_op {
   // set on a shallow copy by the fused CG loop: y[0 .. n_zero) and the dot
   // accumulator were already zeroed by the previous cg_step_kernel
   bool prezeroed = false;
+  // lazy zero fill (sfem_op_set_lazy_zero): device tables owned by the caller,
+  // counters owned by the library.  `lazy_grid` is the grid the tables were
+  // built for; the launcher falls back to the eager fill if its grid differs.
+  const int2* lazy_pieces = nullptr;
+  const int32_t* lazy_chunk_ptr = nullptr;
+  unsigned* lazy_counters = nullptr;
+  int lazy_num_chunks = 0, lazy_num_pieces = 0;
+  unsigned lazy_grid = 0, lazy_ahead = 0, lazy_report_mask = 0;
+  sfem::LazyHost* lazy_host = nullptr;  // the stream the lazy launches go to
+  // set on a shallow copy: the launcher only reports {elements per CTA step,
+  // grid, LAZY instance compiled} of the launch it would make (table set-up)
+  unsigned* query = nullptr;
+  // set on a shallow copy by op_apply_internal: zero lazily in this launch
+  bool lazy = false;
 };
 
 // Peer-memory all-reduce handle (sfem_halo.cu).

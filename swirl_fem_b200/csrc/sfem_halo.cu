@@ -57,7 +57,8 @@ int launch_apply3d_halo(const sfem_op& op, double lambda, double mu,
                         cudaStream_t stream);
 int op_apply_internal(const sfem_op* op, double lambda, double mu,
                       const void* x, void* y, int ncomp, double* dot_xy,
-                      cudaStream_t stream, bool prezeroed = false);
+                      cudaStream_t stream, bool prezeroed = false,
+                      bool dot_prezeroed = false);
 bool pdl_enabled();
 
 namespace {

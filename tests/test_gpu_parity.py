@@ -1110,3 +1110,59 @@ def test_no_cpu_fallback():
   with pytest.raises(_lib.SwirlB200Error, match='no CPU path'):
     gs.gather(torch.zeros(4, dtype=torch.float64),
               torch.zeros(2, dtype=torch.int32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+@pytest.mark.parametrize('seed', [None, 3], ids=['natural', 'shuffled'])
+def test_lazy_zero_fill_matches_eager(seed, dtype):
+  """`sfem_op_set_lazy_zero`: the companion kernel zeroes y's shared dofs while
+  the apply runs.  Same results as the eager fill -- on a poisoned output, on
+  repeated launches (the counters are reset by the companion), with the dot
+  product, with the mass term, and inside the fused CG loop (same iteration
+  count) -- on the natural and on a shuffled element order (fragmented id
+  runs, thousands of small pieces)."""
+  from swirl_fem_b200.linalg.cg import cg
+  from swirl_fem_b200.core.operator import JacobiPreconditioner
+  n1d, ne = 8, 16   # 4096 elements: several rounds of CTA steps
+  from swirl_fem_b200.core.fespace import FiniteElementSpace
+  from swirl_fem_b200.core.interpolation import Quadrature1D
+  refined = helpers.deformed_premesh(3, ne, n1d, seed=seed, reorient=False)
+  mesh = refined.finalize(dtype=dtype)
+  space = FiniteElementSpace.create(mesh, Quadrature1D.create(n1d, GLL))
+  bmask = refined.finalize_host()['physical_masks']['boundary']
+  op = space.operator(dirichlet_mask=bmask, with_mass=True)
+  dev = mesh.device
+  gen = torch.Generator(device='cpu').manual_seed(5)
+  x = torch.randn(mesh.num_nodes, generator=gen, dtype=torch.float64).to(
+      dev, dtype)
+  dot_e = torch.zeros((), dtype=torch.float64, device=dev)
+  y_e = op.apply(x, lam=0.7, mu=1.3, dot_out=dot_e).clone()
+  rhs = op.apply(torch.ones_like(x), lam=1.0, mu=0.0)
+  M = JacobiPreconditioner(op.diag(lam=0.0, mu=1.0))
+  tol = 1e-8 if dtype == torch.float64 else 1e-4
+  xe, info_e = cg(op.bind(0.0, 1.0), rhs, tol=tol, M=M, maxiter=400)
+  assert op.enable_lazy_zero(ahead=4.0, report_every=4)
+  eps = 1e-13 if dtype == torch.float64 else 2e-5
+  scale = float(y_e.abs().max())
+  for rep in range(4):
+    out = torch.full_like(x, float('nan'))
+    dot_l = torch.full((), float('nan'), dtype=torch.float64, device=dev)
+    y_l = op.apply(x, lam=0.7, mu=1.3, out=out, dot_out=dot_l)
+    assert float((y_l - y_e).abs().max()) <= eps * scale, rep
+    assert abs(float(dot_l) - float(dot_e)) <= 10 * eps * abs(float(dot_e))
+  xl, info_l = cg(op.bind(0.0, 1.0), rhs, tol=tol, M=M, maxiter=400)
+  assert abs(info_l['num_iterations'] - info_e['num_iterations']) <= 1
+  # (two solves to a relative residual of `tol` with different summation orders)
+  assert float((xl - xe).abs().max()) <= 1e3 * tol * float(xe.abs().max())
+  assert not op.lazy_zero_timed_out()
+  # other pacing parameters, and back to the eager fill
+  assert op.enable_lazy_zero(ahead=2.0, report_every=1)
+  out = torch.full_like(x, float('nan'))
+  assert float((op.apply(x, lam=0.7, mu=1.3, out=out) - y_e).abs().max()) \
+      <= eps * scale
+  assert not op.lazy_zero_timed_out()
+  op.disable_lazy_zero()
+  out = torch.full_like(x, float('nan'))
+  assert float((op.apply(x, lam=0.7, mu=1.3, out=out) - y_e).abs().max()) \
+      <= eps * scale
