@@ -250,23 +250,26 @@ int sfem_op_set_variant(sfem_op* op, int32_t variant);
  * prefix before its kernel; for a prefix much larger than L2 this costs two
  * extra DRAM accesses per shared dof.  With the tables below a COMPANION
  * kernel zeroes every shared dof shortly before the first element that
- * touches it is scattered, while the apply runs (3-D collocated operators
- * with a compiled instance, ncomp == 1; otherwise the eager fill stays).
+ * touches it is scattered, while the apply runs, and the apply's CTAs claim
+ * their element steps from a counter (one tight window of consecutive steps)
+ * instead of striding through them (3-D collocated operators with a compiled
+ * instance, ncomp == 1; otherwise the eager fill stays).
  *   sfem_op_lazy_zero_query: elements per CTA step and grid of the launch
  *     sfem_op_apply would make; *supported = 1 if a lazy instance exists.
- *   sfem_op_set_lazy_zero: `pieces` device int32 (num_pieces, 2) = {first
+ *   sfem_op_set_lazy_zero: the elements are cut into chunks of `chunk_steps`
+ *     consecutive CTA steps; `pieces` device int32 (num_pieces, 2) = {first
  *     dof, length | chunk << 12} ranges (length <= 4095) covering [0, n_zero)
- *     exactly once, sorted by chunk, where chunk j = the dofs first touched by CTA steps [j * grid,
- *     (j + 1) * grid) (dofs no element touches: chunk 0); `chunk_ptr` device
- *     int32 (num_chunks + 1) = first piece of every chunk; the companion
- *     runs at most `ahead_steps` CTA steps ahead of the apply's progress,
- *     which its CTAs report every `report_every`-th step (1, 2, 4 or 8;
- *     ahead_steps >= report_every * grid).  The tables are retained (caller
- *     keeps them alive); chunk_ptr == NULL switches back to the eager fill.
- *     The lazy launches of one handle must all go to ONE stream (other
- *     streams use the eager fill).
+ *     exactly once, sorted by chunk, where chunk j = the dofs first touched
+ *     by CTA steps [j * chunk_steps, (j + 1) * chunk_steps) (dofs no element
+ *     touches: chunk 0); `chunk_ptr` device int32 (num_chunks + 1) = first
+ *     piece of every chunk; a chunk is zeroed `ahead_steps` steps before its
+ *     first step is claimed (a step is claimed three steps before it runs).
+ *     The tables are retained (caller keeps them alive); chunk_ptr == NULL
+ *     switches back to the eager fill.  The lazy launches of one handle must
+ *     all go to ONE stream (other streams use the eager fill).
  *   sfem_op_lazy_zero_timed_out: 1 if a device-side wait of the protocol ever
- *     hit its 2 s limit (results since then are invalid); synchronises. */
+ *     hit its 2 s limit (results since then are invalid; sfem_last_error
+ *     tells which wait); synchronises. */
 /* Number of leading entries of y that several elements accumulate into (the
  * prefix that must be zero before an apply). */
 int64_t sfem_op_num_zero(const sfem_op* op);
@@ -274,8 +277,7 @@ int sfem_op_lazy_zero_query(const sfem_op* op, int32_t* step_elems,
                             int32_t* grid, int32_t* supported);
 int sfem_op_set_lazy_zero(sfem_op* op, const void* pieces, int64_t num_pieces,
                           const void* chunk_ptr, int32_t num_chunks,
-                          int32_t grid, int64_t ahead_steps,
-                          int32_t report_every);
+                          int32_t chunk_steps, int32_t ahead_steps);
 int sfem_op_lazy_zero_timed_out(const sfem_op* op, sfem_stream_t stream);
 
 /* ------------------------------------------------------------------------ */

@@ -154,7 +154,7 @@ SIGNATURES = {
         _c_ptr, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
         ctypes.POINTER(ctypes.c_int32)]),
     'sfem_op_set_lazy_zero': (ctypes.c_int, [_c_ptr, _c_ptr, _c_i64, _c_ptr,
-                                             _c_i32, _c_i32, _c_i64, _c_i32]),
+                                             _c_i32, _c_i32, _c_i32]),
     'sfem_op_lazy_zero_timed_out': (ctypes.c_int, [_c_ptr, _c_ptr]),
     'sfem_cg_workspace_bytes': (_c_i64, [ctypes.c_int, _c_i64]),
     'sfem_cg': (ctypes.c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr,

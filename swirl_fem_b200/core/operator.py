@@ -78,22 +78,19 @@ class FusedOperator:
     self.num_nodes = mesh.num_nodes
     self.ndim = mesh.ndim
     self._lazy = None
-    # SFEM_LAZY_ZERO: 0 never, 1 whenever a lazy instance exists, default: when
-    # the shared-dof prefix is larger than half of L2 (the eager fill's zeros
-    # are then evicted before the first accumulation reaches them)
-    mode = os.environ.get('SFEM_LAZY_ZERO', 'auto')
-    if mode != '0' and mesh.ndim == 3 and interp.collocated:
-      nz = int(lib.sfem_op_num_zero(handle))
-      if mode == '1' or nz * esz >= (64 << 20):
-        self.enable_lazy_zero()
+    # SFEM_LAZY_ZERO=1: zero y's shared dofs lazily where a kernel instance
+    # exists (see enable_lazy_zero); default: the eager fill before the apply
+    if (os.environ.get('SFEM_LAZY_ZERO', '0') == '1' and mesh.ndim == 3
+        and interp.collocated):
+      self.enable_lazy_zero()
 
-  def enable_lazy_zero(self, ahead: float | None = None,
-                       report_every: int | None = None,
-                       piece: int = 1024) -> bool:
-    """Builds the tables of the lazy zero fill (`sfem_op_set_lazy_zero`): a
-    companion kernel then zeroes y's shared dofs while the apply runs, each
-    shortly before its first accumulation (see `lazy_zero_tables`).  `ahead`:
-    how many rounds of CTA steps the companion may run ahead of the apply.
+  def enable_lazy_zero(self, chunk_steps: int | None = None,
+                       ahead: int | None = None, piece: int = 1024) -> bool:
+    """Builds the tables of the lazy zero fill (`sfem_op_set_lazy_zero`): the
+    apply's CTAs then claim their element steps from a counter, and a
+    companion kernel zeroes y's shared dofs while the apply runs, each shortly
+    before its first accumulation (see `lazy_zero_tables`).  `chunk_steps`:
+    CTA steps per chunk; `ahead`: extra lead of the companion in steps.
     Returns False -- the eager fill stays -- when this operator has no lazy
     kernel instance or the mesh is too small."""
     lib = _lib.lib()
@@ -103,29 +100,29 @@ class FusedOperator:
                 'sfem_op_lazy_zero_query')
     if not sup.value:
       return False
+    if chunk_steps is None:
+      chunk_steps = int(os.environ.get('SFEM_LAZY_CHUNK', 128))
     if ahead is None:
-      ahead = float(os.environ.get('SFEM_LAZY_AHEAD', 4))
-    if report_every is None:
-      report_every = int(os.environ.get('SFEM_LAZY_REPORT', 4))
+      ahead = int(os.environ.get('SFEM_LAZY_AHEAD', 0))
+    if self.mesh.num_elements < 4 * grid.value * se.value:
+      return False   # a couple of waves at least
     tables = lazy_zero_tables(
         self.mesh.elements, self.num_nodes,
-        int(lib.sfem_op_num_zero(self.handle)), se.value, grid.value, piece)
+        int(lib.sfem_op_num_zero(self.handle)), se.value, chunk_steps, piece)
     if tables is None:
       return False
     pieces, chunk_ptr = tables
-    ahead_steps = max(int(round(ahead * grid.value)),
-                      report_every * grid.value)
     with torch.cuda.device(pieces.device):
       _lib._check(lib.sfem_op_set_lazy_zero(
           self.handle, _lib.ptr(pieces), int(pieces.shape[0]),
-          _lib.ptr(chunk_ptr), int(chunk_ptr.numel() - 1), grid.value,
-          ahead_steps, report_every), 'sfem_op_set_lazy_zero')
+          _lib.ptr(chunk_ptr), int(chunk_ptr.numel() - 1), int(chunk_steps),
+          int(ahead)), 'sfem_op_set_lazy_zero')
     self._lazy = (pieces, chunk_ptr)   # the C side retains these pointers
     return True
 
   def disable_lazy_zero(self):
     _lib._check(_lib.lib().sfem_op_set_lazy_zero(
-        self.handle, None, 0, None, 0, 0, 0, 1), 'sfem_op_set_lazy_zero')
+        self.handle, None, 0, None, 0, 0, 0), 'sfem_op_set_lazy_zero')
     self._lazy = None
 
   def lazy_zero_timed_out(self) -> str:
@@ -279,23 +276,23 @@ class FusedOperator:
 
 
 def lazy_zero_tables(elements: torch.Tensor, num_nodes: int, num_zero: int,
-                     step_elems: int, grid: int, piece: int = 2048):
+                     step_elems: int, chunk_steps: int, piece: int = 1024):
   """Tables of the lazy zero fill (see `sfem_op_set_lazy_zero`).
 
-  The apply's persistent CTAs run their j-th step at about the same time (CTA b
-  processes steps b, b + grid, ...), so the elements are cut into chunks of
-  `grid` steps = `grid * step_elems` elements; every dof of the shared prefix
-  [0, num_zero) belongs to the chunk that touches it FIRST (dofs no element
-  touches: chunk 0).  Returns `(pieces int32 (P, 2) = {first dof, length |
-  chunk << 12}, chunk_ptr int32 (num_chunks + 1,))` -- pieces sorted by chunk, never
-  crossing a chunk boundary or a gap in the ids, at most `piece` dofs long --
-  or None when there are fewer than 4 chunks.  Index arithmetic only (torch,
-  any device; set-up time)."""
+  The lazy apply's CTAs claim consecutive element steps (`step_elems` elements
+  each) from a counter, so the elements are cut into chunks of `chunk_steps`
+  steps = `chunk_steps * step_elems` consecutive elements; every dof of the
+  shared prefix [0, num_zero) belongs to the chunk that touches it FIRST (dofs
+  no element touches: chunk 0).  Returns `(pieces int32 (P, 2) = {first dof,
+  length | chunk << 12}, chunk_ptr int32 (num_chunks + 1,))` -- pieces sorted
+  by chunk, never crossing a chunk boundary or a gap in the ids, at most
+  `piece` dofs long -- or None when there are fewer than 4 chunks.  Index
+  arithmetic only (torch, any device; set-up time)."""
   E, n = int(elements.shape[0]), int(elements.shape[1])
-  if (step_elems <= 0 or grid <= 0 or num_zero <= 0 or num_nodes >= 2 ** 31
-      or not 1 <= piece <= 4095):
+  if (step_elems <= 0 or chunk_steps <= 0 or num_zero <= 0
+      or num_nodes >= 2 ** 31 or not 1 <= piece <= 4095):
     return None
-  chunk_elems = grid * step_elems
+  chunk_elems = chunk_steps * step_elems
   num_chunks = -(-E // chunk_elems)
   if num_chunks < 4 or num_chunks >= (1 << 19):
     return None

@@ -384,8 +384,7 @@ int sfem_op_lazy_zero_query(const sfem_op* op, int32_t* step_elems,
 
 int sfem_op_set_lazy_zero(sfem_op* op, const void* pieces, int64_t num_pieces,
                           const void* chunk_ptr, int32_t num_chunks,
-                          int32_t grid, int64_t ahead_steps,
-                          int32_t report_every) {
+                          int32_t chunk_steps, int32_t ahead_steps) {
   using namespace sfem;
   SFEM_REQUIRE(op != nullptr, "null argument");
   if (chunk_ptr == nullptr) {  // back to the eager fill
@@ -395,22 +394,16 @@ int sfem_op_set_lazy_zero(sfem_op* op, const void* pieces, int64_t num_pieces,
     return SFEM_OK;
   }
   SFEM_REQUIRE(pieces && num_pieces >= 0 && num_pieces < (1ll << 31) &&
-                   num_chunks >= 2 && grid > 0,
+                   num_chunks >= 2 && num_chunks < (1 << 19) &&
+                   chunk_steps > 0 && ahead_steps >= 0,
                "bad lazy zero tables");
-  SFEM_REQUIRE(report_every == 1 || report_every == 2 || report_every == 4 ||
-                   report_every == 8,
-               "report_every must be 1, 2, 4 or 8");
-  // the progress counter moves in units of report_every steps per CTA: the
-  // pacing window must cover that, or the last chunks would never be released
-  SFEM_REQUIRE(ahead_steps >= (int64_t)report_every * grid &&
-                   ahead_steps < (1ll << 31),
-               "ahead_steps must be at least report_every * grid");
   int32_t se = 0, g = 0, sup = 0;
   int rc = sfem_op_lazy_zero_query(op, &se, &g, &sup);
   if (rc) return rc;
-  SFEM_REQUIRE(sup == 1 && g == grid,
-               "lazy zero fill: not supported for this operator, or the tables "
-               "were built for another grid");
+  SFEM_REQUIRE(sup == 1, "lazy zero fill: no kernel instance for this operator");
+  const int64_t steps = (op->base.desc.num_elements + se - 1) / se;
+  SFEM_REQUIRE((steps + chunk_steps - 1) / chunk_steps == num_chunks,
+               "lazy zero fill: num_chunks does not match chunk_steps");
   if (op->lazy_counters) {
     SFEM_CUDA_CHECK(cudaDeviceSynchronize());
     SFEM_CUDA_CHECK(cudaFree(op->lazy_counters));
@@ -428,9 +421,9 @@ int sfem_op_set_lazy_zero(sfem_op* op, const void* pieces, int64_t num_pieces,
   op->lazy_chunk_ptr = (const int32_t*)chunk_ptr;
   op->lazy_num_chunks = num_chunks;
   op->lazy_num_pieces = (int)num_pieces;
-  op->lazy_grid = (unsigned)grid;
+  op->lazy_step_elems = (unsigned)se;
+  op->lazy_chunk_steps = (unsigned)chunk_steps;
   op->lazy_ahead = (unsigned)ahead_steps;
-  op->lazy_report_mask = (unsigned)report_every - 1u;
   return SFEM_OK;
 }
 
@@ -449,9 +442,9 @@ int sfem_op_lazy_zero_timed_out(const sfem_op* op, sfem_stream_t stream) {
     char msg[256];
     snprintf(msg, sizeof(msg),
              "lazy zero fill: first timeout in %s %u at chunk %u (saw %u, "
-             "progress counter %u; grid %u, chunks %d)",
-             dbg[0] == 1 ? "apply CTA" : "companion warp", dbg[1], dbg[2],
-             dbg[3], dbg[4], op->lazy_grid, op->lazy_num_chunks);
+             "claim counter %u; chunk steps %u, chunks %d)",
+             dbg[0] == 1 ? "apply CTA" : "companion CTA", dbg[1], dbg[2],
+             dbg[3], dbg[4], op->lazy_chunk_steps, op->lazy_num_chunks);
     sfem::set_error(msg);
   }
   return v != 0;

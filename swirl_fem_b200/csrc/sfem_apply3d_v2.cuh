@@ -317,12 +317,24 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     else
       bulk_copy_g2s(sG0, gf + first * (int64_t)(ngeom * n), bytes, &gbar);
   };
+  // LAZY: the CTA steps after the first wave are CLAIMED from a counter (three
+  // steps ahead, so that connectivity and factors can be prefetched) instead
+  // of strided: the CTAs then work on one tight window of consecutive steps
+  // -- what the companion's pacing and the L2 residency of its zeros need.
+  // s_lz[0]: "this step's chunk is zeroed", s_lz[1]: the ticket just claimed.
+  __shared__ unsigned s_lz[2];
+  if (LAZY && threadIdx.x == 0) s_lz[1] = atomicAdd(&lz.counters[0], 2u);
   if (STAGE) {
     if (threadIdx.x == 0) mbar_init(&gbar, 1);
     mbar_fence_init();
     __syncthreads();
     if (threadIdx.x == 0 && blk < nblocks) stage_copy(blk);
+  } else if (LAZY) {
+    __syncthreads();
   }
+  // the steps after `blk`
+  int64_t blk1 = LAZY ? (int64_t)gridDim.x + s_lz[1] : blk + gridDim.x;
+  int64_t blk2 = LAZY ? blk1 + 1 : blk1 + gridDim.x;
 
   // prologue: gather of the first element into u tile 0
 #pragma unroll
@@ -378,7 +390,6 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
   // CONN2: connectivity of the NEXT step, carried across iterations
   uint32_t nrc_c[CONN2 ? N : 1];
   if constexpr (CONN2 && !LOCAL) {
-    const int64_t blk1 = blk + gridDim.x;
     const int64_t e1 = blk1 * epb + slot;
     const bool a1 = lane_ok && blk1 < nblocks && e1 < E;
 #pragma unroll
@@ -386,21 +397,23 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       nrc_c[k] = a1 ? ld_stream(conn + e1 * n + k * P + t) : kConnSentinel;
   }
 
-  // LAZY: this CTA's step number is its chunk index
-  __shared__ unsigned s_lz;
-  unsigned lz_it = 0, lz_seen = 0, lz_need = 0;
+  // LAZY (thread 0): chunk of this step, its count when last looked at, the
+  // number of its pieces, the ticket in flight
+  unsigned lz_c = 0, lz_seen = 0, lz_need = 0, lz_ticket = 0;
 
   int buf = 0;
-  for (; blk < nblocks; blk += gridDim.x, buf ^= 1) {
+  for (; blk < nblocks; buf ^= 1) {
     T* sU = sU0 + buf * C::tile;
     T* sUn = sU0 + (buf ^ 1) * C::tile;
     if (LAZY && threadIdx.x == 0) {
-      lz_seen = ld_relaxed_gpu(&lz.counters[2 + lz_it]);
-      lz_need = (unsigned)(__ldg(lz.chunk_ptr + lz_it + 1) -
-                           __ldg(lz.chunk_ptr + lz_it));
+      lz_ticket = atomicAdd(&lz.counters[0], 1u);  // the step after blk2
+      lz_c = (unsigned)blk / lz.chunk_steps;
+      lz_seen = ld_relaxed_gpu(&lz.counters[2 + lz_c]);
+      lz_need = (unsigned)(__ldg(lz.chunk_ptr + lz_c + 1) -
+                           __ldg(lz.chunk_ptr + lz_c));
     }
     // ---- pipeline: next element's factors -> L2, connectivity -> registers
-    const int64_t blk_n = blk + gridDim.x;
+    const int64_t blk_n = blk1;
     const int64_t e_n = blk_n * epb + slot;
     const bool active_n = lane_ok && blk_n < nblocks && e_n < E;
     uint32_t nrc[N];
@@ -409,7 +422,7 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
     if constexpr (CONN2 && !LOCAL) {
       // this step's "next" words arrived a whole step ago; fetch the ones of
       // the step after it
-      const int64_t blk_nn = blk_n + gridDim.x;
+      const int64_t blk_nn = blk2;
       const int64_t e_nn = blk_nn * epb + slot;
       const bool active_nn = lane_ok && blk_nn < nblocks && e_nn < E;
 #pragma unroll
@@ -603,7 +616,10 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
         for (int k = 0; k < N; ++k) ry[k] += ucol[k];
       }
     }
-    if (LAZY && threadIdx.x == 0) s_lz = lz_seen >= lz_need;
+    if (LAZY && threadIdx.x == 0) {
+      s_lz[0] = lz_seen >= lz_need;
+      s_lz[1] = lz_ticket;
+    }
     __syncthreads();
     if (STAGE) {
       // every thread of the slot is done reading the staged factors: refill
@@ -635,16 +651,16 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
       // again before the next step's barriers.)  The relaxed poll suffices on
       // the fast path: the zeros were fenced before the count, and the REDs
       // below are L2 operations issued after the count was seen.
-      if (!s_lz) {
+      if (!s_lz[0]) {
         if (threadIdx.x == 0 && ld_relaxed_gpu(&lz.counters[1]) == 0 &&
-            !spin_u32_relaxed_ge(&lz.counters[2 + lz_it], lz_need, 250,
+            !spin_u32_relaxed_ge(&lz.counters[2 + lz_c], lz_need, 250,
                                  2000000000ull)) {
           // sticky: later steps do not wait again.  First failure: who / what
           unsigned* dbg = lz.counters + 2 + lz.num_chunks;
           if (atomicCAS(dbg, 0u, 1u) == 0u) {
             dbg[1] = blockIdx.x;
-            dbg[2] = lz_it;
-            dbg[3] = ld_relaxed_gpu(&lz.counters[2 + lz_it]);
+            dbg[2] = lz_c;
+            dbg[3] = ld_relaxed_gpu(&lz.counters[2 + lz_c]);
             dbg[4] = ld_relaxed_gpu(&lz.counters[0]);
           }
           lz.counters[1] = 1u;
@@ -687,12 +703,10 @@ apply3d_v2_kernel(const __grid_constant__ DOps<T, N> dm,
 #pragma unroll
     for (int k = 0; k < N; ++k) rc[k] = nrc[k];
     if (HALO && hstate == kHIface && blk_n >= hd.n_if_blocks) __threadfence();
-    if (LAZY) {
-      // progress report (a hint for the companion's pacing: no ordering needed)
-      ++lz_it;
-      if (threadIdx.x == 0 && (lz_it & lz.report_mask) == 0)
-        red_add_u32(&lz.counters[0], lz.report_mask + 1u);
-    }
+    // next step (LAZY: s_lz[1] was written before the barrier after phase 3)
+    blk = blk1;
+    blk1 = blk2;
+    blk2 = LAZY ? (int64_t)gridDim.x + s_lz[1] : blk2 + gridDim.x;
   }
   cp_async_wait_all();
   if (HALO) {
@@ -765,12 +779,16 @@ lazy_zero_kernel(T* __restrict__ y, const LazyDev lz) {
     if (p >= lz.num_pieces) break;
     const int2 pc = __ldg(lz.pieces + p);
     const unsigned j = (unsigned)pc.y >> 12;
-    const uint64_t need = (uint64_t)j * lz.grid;
-    if (need > lz.ahead && !dead) {
+    // steps claimed so far = grid + counters[0] (a step is claimed three steps
+    // before it runs); chunk j is due once its first step is `ahead` steps
+    // from being claimed
+    const uint64_t need = (uint64_t)j * lz.chunk_steps;
+    const uint64_t have = (uint64_t)lz.grid + lz.ahead;
+    if (need > have && !dead) {
       int ok = 1;
       if (lane == 0)
-        ok = spin_u32_relaxed_ge(&lz.counters[0], (unsigned)(need - lz.ahead),
-                                 1000, 2000000000ull);
+        ok = spin_u32_relaxed_ge(&lz.counters[0], (unsigned)(need - have), 500,
+                                 2000000000ull);
       ok = __shfl_sync(0xffffffffu, ok, 0);
       if (!ok) {
         dead = true;  // the apply made no progress: zero the rest unpaced
@@ -779,7 +797,7 @@ lazy_zero_kernel(T* __restrict__ y, const LazyDev lz) {
           if (atomicCAS(dbg, 0u, 2u) == 0u) {
             dbg[1] = blockIdx.x;
             dbg[2] = j;
-            dbg[3] = (unsigned)(need - lz.ahead);
+            dbg[3] = (unsigned)(need - have);
             dbg[4] = ld_relaxed_gpu(&lz.counters[0]);
           }
           lz.counters[1] = 1u;
@@ -863,7 +881,8 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
   LazyDev lz{};
   unsigned lazy_ctas = 0;
   if (LAZY) {
-    if (op.lazy_grid != grid.x || ncomp != 1 || op.lazy_counters == nullptr) {
+    if (op.lazy_step_elems != (unsigned)C::epb || ncomp != 1 ||
+        op.lazy_counters == nullptr || nblocks >= (1ll << 31)) {
       set_error("lazy zero fill: tables were built for another launch geometry");
       return SFEM_ERR_INVALID;
     }
@@ -891,7 +910,7 @@ int launch3d_v2_cfg(const sfem_op& op, double lambda, double mu, const void* x,
     lz.num_chunks = op.lazy_num_chunks;
     lz.grid = grid.x;
     lz.ahead = op.lazy_ahead;
-    lz.report_mask = op.lazy_report_mask;
+    lz.chunk_steps = op.lazy_chunk_steps;
     lz.num_pieces = op.lazy_num_pieces;
   }
   DOps<T, N> dm;

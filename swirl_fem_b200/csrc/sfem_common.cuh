@@ -413,20 +413,26 @@ __device__ __forceinline__ bool scalar_allreduce_warp(const ScalarDev& sx,
 // so that it runs next to it) -- not the apply's own CTAs: four in-kernel
 // variants reached 0.998 x the algorithmic DRAM traffic but ran 15-45 % slower
 // (fences in the element CTAs, CTAs coupled to one another).
-// The apply's persistent CTAs all execute their j-th step at about the same
-// time (CTA b runs steps b, b + G, b + 2G, ...), so the unit is "chunk j" =
-// the dofs first touched by steps [jG, (j+1)G).  Tables (host-built,
-// sfem_op_set_lazy_zero): `pieces` = {first dof, len | chunk << 12}, sorted by
-// chunk, a work queue for the companion's warps; `chunk_ptr[j]` = first piece
-// of chunk j (dofs no element touches are zeroed with chunk 0).  Protocol on
-// `counters`:
-//   [0]      steps completed by the apply's CTAs (fire-and-forget RED per step);
-//            a piece of chunk j is zeroed once [0] + ahead >= j * G, i.e. a few
-//            steps before it is needed, never further ahead
+//
+// When: the LAZY apply instance does not stride its CTA steps; after the first
+// wave (step b for CTA b) every CTA CLAIMS its steps from a counter, three
+// steps before it runs them.  The CTAs therefore work on one tight window of
+// consecutive steps, and the counter tells the companion exactly how far the
+// apply is: the elements are cut into chunks of `chunk_steps` consecutive
+// steps, chunk j = the dofs FIRST touched by steps [j S, (j+1) S), and a chunk
+// is zeroed when its first step is about to be claimed.  (With strided steps
+// the CTAs drift apart by many steps: either the companion runs far ahead and
+// its zeros are evicted again, or the fast CTAs wait -- measured, no gain.)
+//
+// Tables (host-built, sfem_op_set_lazy_zero): `pieces` = {first dof, len |
+// chunk << 12}, sorted by chunk, a work queue for the companion's warps;
+// `chunk_ptr[j]` = first piece of chunk j (dofs no element touches are zeroed
+// with chunk 0).  Protocol on `counters`:
+//   [0]      steps claimed after the first wave (atomicAdd by the apply's CTAs)
 //   [1]      sticky: a wait timed out (the result is invalid)
 //   [2 + j]  pieces of chunk j that are zeroed (the warp fences, then counts);
-//            a CTA scatters its step j only after [2 + j] == the number of
-//            pieces of chunk j (relaxed poll issued at the top of the step,
+//            a CTA scatters a step of chunk j only after [2 + j] == the number
+//            of pieces of chunk j (relaxed poll issued at the top of the step,
 //            looked at before phase 5)
 //   [2 + num_chunks ..]  8 words: record of the first timed-out wait; then the
 //            queue head and the count of companion CTAs that are done
@@ -438,11 +444,11 @@ __device__ __forceinline__ bool scalar_allreduce_warp(const ScalarDev& sx,
 struct LazyDev {
   const int2* pieces;
   const int32_t* chunk_ptr;  // (num_chunks + 1)
-  unsigned* counters;        // 2 + num_chunks words
+  unsigned* counters;
   int num_chunks;
-  unsigned grid;             // G: the apply's grid (CTA steps per chunk)
-  unsigned ahead;            // in CTA steps, see [0]
-  unsigned report_mask;      // a CTA reports every (mask + 1)-th step
+  unsigned grid;             // the apply's grid = size of the first wave
+  unsigned ahead;            // extra lead of the companion, in CTA steps
+  unsigned chunk_steps;      // S
   int num_pieces;
 };
 
@@ -561,13 +567,13 @@ struct sfem_op {
   // accumulator were already zeroed by the previous cg_step_kernel
   bool prezeroed = false;
   // lazy zero fill (sfem_op_set_lazy_zero): device tables owned by the caller,
-  // counters owned by the library.  `lazy_grid` is the grid the tables were
-  // built for; the launcher falls back to the eager fill if its grid differs.
+  // counters owned by the library.  `lazy_step_elems`: elements per CTA step
+  // the tables were built for (checked by the launcher).
   const int2* lazy_pieces = nullptr;
   const int32_t* lazy_chunk_ptr = nullptr;
   unsigned* lazy_counters = nullptr;
   int lazy_num_chunks = 0, lazy_num_pieces = 0;
-  unsigned lazy_grid = 0, lazy_ahead = 0, lazy_report_mask = 0;
+  unsigned lazy_step_elems = 0, lazy_chunk_steps = 0, lazy_ahead = 0;
   sfem::LazyHost* lazy_host = nullptr;  // the stream the lazy launches go to
   // set on a shallow copy: the launcher only reports {elements per CTA step,
   // grid, LAZY instance compiled} of the launch it would make (table set-up)

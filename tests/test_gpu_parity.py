@@ -1116,8 +1116,9 @@ def test_no_cpu_fallback():
 @pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
 @pytest.mark.parametrize('seed', [None, 3], ids=['natural', 'shuffled'])
 def test_lazy_zero_fill_matches_eager(seed, dtype):
-  """`sfem_op_set_lazy_zero`: the companion kernel zeroes y's shared dofs while
-  the apply runs.  Same results as the eager fill -- on a poisoned output, on
+  """`sfem_op_set_lazy_zero`: the apply's CTAs claim their steps from a counter
+  and the companion kernel zeroes y's shared dofs while the apply runs.  Same
+  results as the eager fill -- on a poisoned output, on
   repeated launches (the counters are reset by the companion), with the dot
   product, with the mass term, and inside the fused CG loop (same iteration
   count) -- on the natural and on a shuffled element order (fragmented id
@@ -1142,7 +1143,7 @@ def test_lazy_zero_fill_matches_eager(seed, dtype):
   M = JacobiPreconditioner(op.diag(lam=0.0, mu=1.0))
   tol = 1e-8 if dtype == torch.float64 else 1e-4
   xe, info_e = cg(op.bind(0.0, 1.0), rhs, tol=tol, M=M, maxiter=400)
-  assert op.enable_lazy_zero(ahead=4.0, report_every=4)
+  assert op.enable_lazy_zero()
   eps = 1e-13 if dtype == torch.float64 else 2e-5
   scale = float(y_e.abs().max())
   for rep in range(4):
@@ -1157,7 +1158,7 @@ def test_lazy_zero_fill_matches_eager(seed, dtype):
   assert float((xl - xe).abs().max()) <= 1e3 * tol * float(xe.abs().max())
   assert not op.lazy_zero_timed_out()
   # other pacing parameters, and back to the eager fill
-  assert op.enable_lazy_zero(ahead=2.0, report_every=1)
+  assert op.enable_lazy_zero(chunk_steps=37, ahead=50, piece=200)
   out = torch.full_like(x, float('nan'))
   assert float((op.apply(x, lam=0.7, mu=1.3, out=out) - y_e).abs().max()) \
       <= eps * scale

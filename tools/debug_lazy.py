@@ -24,9 +24,7 @@ dev = mesh.device
 x = torch.randn(mesh.num_nodes, dtype=torch.float64, device=dev)
 lam = 0.7 if with_mass else 0.0
 y_e = op.apply(x, lam=lam, mu=1.3).clone()
-ok = op.enable_lazy_zero(ahead=float(os.environ.get('AHEAD', 4)),
-                         report_every=int(os.environ.get('REPORT', 4)),
-                         piece=piece)
+ok = op.enable_lazy_zero(piece=piece)
 print('enabled', ok, 'pieces', op._lazy[0].shape, 'chunks', op._lazy[1].numel() - 1)
 pieces, cp = op._lazy[0].cpu().numpy(), op._lazy[1].cpu().numpy()
 nz = int(_lib.lib().sfem_op_num_zero(op.handle))

@@ -1,6 +1,7 @@
 #!/usr/bin/env bash
-# Round-2 GPU job 12 (1 GPU): lazy zero fill by a companion kernel -- test,
-# then the bench line with the eager fill and with several pacings.
+# Round-2 GPU job 12 (1 GPU): lazy zero fill by a companion kernel + claimed
+# CTA steps -- test, then the bench line with the eager fill and with several
+# chunk sizes / leads.
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
@@ -27,12 +28,10 @@ except Exception as e:
 PY
 }
 run eager SFEM_LAZY_ZERO=0
-run a6_r4 SFEM_LAZY_ZERO=1 SFEM_LAZY_AHEAD=6 SFEM_LAZY_REPORT=4 || { echo "lazy path broken: stopping"; cat $O/r2_lazy_a6_r4.err | tail -5; exit 0; }
-run a4_r4 SFEM_LAZY_ZERO=1 SFEM_LAZY_AHEAD=4 SFEM_LAZY_REPORT=4
-run a3_r2 SFEM_LAZY_ZERO=1 SFEM_LAZY_AHEAD=3 SFEM_LAZY_REPORT=2
-run a2_r2 SFEM_LAZY_ZERO=1 SFEM_LAZY_AHEAD=2 SFEM_LAZY_REPORT=2
-run a3_r1 SFEM_LAZY_ZERO=1 SFEM_LAZY_AHEAD=3 SFEM_LAZY_REPORT=1 || { echo "r1 broken: stopping"; cat $O/r2_lazy_a3_r1.err | tail -5; exit 0; }
-run a2_r1 SFEM_LAZY_ZERO=1 SFEM_LAZY_AHEAD=2 SFEM_LAZY_REPORT=1
-run a1_r1 SFEM_LAZY_ZERO=1 SFEM_LAZY_AHEAD=1 SFEM_LAZY_REPORT=1
-run a3_r1_c74 SFEM_LAZY_ZERO=1 SFEM_LAZY_AHEAD=3 SFEM_LAZY_REPORT=1 SFEM_LAZY_CTAS=74
+run c128_a0 SFEM_LAZY_ZERO=1 SFEM_LAZY_CHUNK=128 SFEM_LAZY_AHEAD=0 || { echo "lazy path broken: stopping"; tail -5 $O/r2_lazy_c128_a0.err; exit 0; }
+run c128_a740 SFEM_LAZY_ZERO=1 SFEM_LAZY_CHUNK=128 SFEM_LAZY_AHEAD=740
+run c512_a0 SFEM_LAZY_ZERO=1 SFEM_LAZY_CHUNK=512 SFEM_LAZY_AHEAD=0
+run c32_a0 SFEM_LAZY_ZERO=1 SFEM_LAZY_CHUNK=32 SFEM_LAZY_AHEAD=0
+run c128_a2200 SFEM_LAZY_ZERO=1 SFEM_LAZY_CHUNK=128 SFEM_LAZY_AHEAD=2200
+run c128_a0_c74 SFEM_LAZY_ZERO=1 SFEM_LAZY_CHUNK=128 SFEM_LAZY_AHEAD=0 SFEM_LAZY_CTAS=74
 echo done
