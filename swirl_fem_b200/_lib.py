@@ -345,10 +345,13 @@ _NUM_UNIQUE = {}  # (data_ptr, numel) of a unique-index tensor -> max + 1
 
 
 def exchange(u: torch.Tensor, gather_indices: torch.Tensor,
-             unique_indices: torch.Tensor | None):
-  """QQ^T over the (periodic) shared dofs; `(G, c)` fields in ONE call."""
+             unique_indices: torch.Tensor | None, inplace: bool = False):
+  """QQ^T over the (periodic) shared dofs; `(G, c)` fields in ONE call.
+  `inplace`: `u` (contiguous) is overwritten instead of copied."""
   require_cuda(u, gather_indices, unique_indices)
-  out = u.contiguous().clone()
+  if inplace and not u.is_contiguous():
+    raise ValueError('in-place exchange needs a contiguous tensor')
+  out = u if inplace else u.contiguous().clone()
   gi = _as_index(gather_indices)
   ui = None if unique_indices is None else _as_index(unique_indices)
   count = gi.numel()

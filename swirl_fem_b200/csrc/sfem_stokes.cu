@@ -30,6 +30,26 @@ struct StokesShape {
   int n, np;       // N^dim, Np^dim
 };
 
+constexpr int cpow_s(int b, int e) { return e <= 0 ? 1 : b * cpow_s(b, e - 1); }
+
+// Compile-time shape (DIM_ > 0) or the runtime one: with constants the
+// contractions unroll, the index arithmetic reduces to shifts / constant
+// multiplies and the 1-D table rows stay in registers.
+template <int DIM_, int N_, int NP_>
+__device__ __forceinline__ StokesShape fix_shape(const StokesShape& s) {
+  if constexpr (DIM_ > 0) {
+    StokesShape f;
+    f.dim = DIM_;
+    f.N = N_;
+    f.Np = NP_;
+    f.n = cpow_s(N_, DIM_);
+    f.np = cpow_s(NP_, DIM_);
+    return f;
+  } else {
+    return s;
+  }
+}
+
 __device__ __forceinline__ int ipow_s(int b, int e) {
   int r = 1;
   for (int i = 0; i < e; ++i) r *= b;
@@ -50,6 +70,7 @@ __device__ __forceinline__ void contract_w(const T* __restrict__ M, int so,
     const int a = idx / (C * O);
     const T* ip = in + a * I * C + c;
     T acc = T(0);
+#pragma unroll
     for (int i = 0; i < I; ++i) acc += M[o * so + i * si] * ip[i * C];
     out[idx] = acc;
   }
@@ -86,15 +107,16 @@ __device__ __forceinline__ T* load_stokes_tables(const StokesShape& s,
   return W + s.N;
 }
 
-template <typename T>
+template <typename T, int DIM_ = 0, int N_ = 0, int NP_ = 0>
 __global__ void __launch_bounds__(32 * kStokesMaxWarps)
-stokes_div_kernel(StokesShape s, const T* __restrict__ vtab,
+stokes_div_kernel(StokesShape s_rt, const T* __restrict__ vtab,
                   const T* __restrict__ ptab,
                   const int32_t* __restrict__ v_el,
                   const int32_t* __restrict__ p_el,
                   const T* __restrict__ invjacs, const T* __restrict__ jacdets,
                   const T* __restrict__ u, int64_t E, int slice,
                   T* __restrict__ out) {
+  const StokesShape s = fix_shape<DIM_, N_, NP_>(s_rt);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* smem = reinterpret_cast<T*>(smem_raw);
   const T* Dv = smem;
@@ -128,6 +150,7 @@ stokes_div_kernel(StokesShape s, const T* __restrict__ vtab,
         for (int j = 0; j < d; ++j) {
           T g = T(0);
           const T* uj = U + j * s.n + base;
+#pragma unroll
           for (int m = 0; m < s.N; ++m) g += Dv[qa * s.N + m] * uj[m * stride];
           div += g * inv[j * d + a];   // grad_j(u_j) = sum_a g_a(u_j) Jinv[j][a]
         }
@@ -156,9 +179,9 @@ stokes_div_kernel(StokesShape s, const T* __restrict__ vtab,
   }
 }
 
-template <typename T>
+template <typename T, int DIM_ = 0, int N_ = 0, int NP_ = 0>
 __global__ void __launch_bounds__(32 * kStokesMaxWarps)
-stokes_grad_t_kernel(StokesShape s, const T* __restrict__ vtab,
+stokes_grad_t_kernel(StokesShape s_rt, const T* __restrict__ vtab,
                      const T* __restrict__ ptab,
                      const int32_t* __restrict__ v_el,
                      const int32_t* __restrict__ p_el,
@@ -166,6 +189,7 @@ stokes_grad_t_kernel(StokesShape s, const T* __restrict__ vtab,
                      const T* __restrict__ jacdets, const T* __restrict__ p,
                      const T* __restrict__ mask, int64_t E, int slice,
                      T* __restrict__ out) {
+  const StokesShape s = fix_shape<DIM_, N_, NP_>(s_rt);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* smem = reinterpret_cast<T*>(smem_raw);
   const T* Dv = smem;
@@ -218,6 +242,7 @@ stokes_grad_t_kernel(StokesShape s, const T* __restrict__ vtab,
         for (int k = 0; k < d; ++k) {
           const T* f = F + (a * d + k) * s.n + base;
           T acc = T(0);
+#pragma unroll
           for (int m = 0; m < s.N; ++m) acc += Dv[m * s.N + na] * f[m * stride];
           y[k] += acc;
         }
@@ -281,9 +306,7 @@ int launch_stokes(K kernel, const StokesShape& s, int slice_elems,
     set_error("fused Stokes operators: element too large for shared memory");
     return SFEM_ERR_UNSUPPORTED;
   }
-  if (smem > 48 * 1024)
-    SFEM_CUDA_CHECK(cudaFuncSetAttribute(
-        kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  (void)kernel;  // the attribute is set per launched instance
   *warps_out = warps;
   *smem_out = smem;
   (void)E;
@@ -309,10 +332,28 @@ int stokes_div_impl(const sfem_space* v, const sfem_space* p, const void* u,
   int64_t blocks = (E + warps - 1) / warps;
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  stokes_div_kernel<T><<<(unsigned)blocks, 32 * warps, smem, stream>>>(
-      s, tables_of<T>(v), tables_of<T>(p), v->base.desc.elements,
-      p->base.desc.elements, (const T*)v->invjacs, (const T*)v->jacdets,
-      (const T*)u, E, slice, (T*)out);
+  auto go = [&](auto kernel) -> int {
+    if (smem > 48 * 1024)
+      SFEM_CUDA_CHECK(cudaFuncSetAttribute(
+          kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<(unsigned)blocks, 32 * warps, smem, stream>>>(
+        s, tables_of<T>(v), tables_of<T>(p), v->base.desc.elements,
+        p->base.desc.elements, (const T*)v->invjacs, (const T*)v->jacdets,
+        (const T*)u, E, slice, (T*)out);
+    return SFEM_OK;
+  };
+  // specialised shapes: the Stokes pairs (N, N - 2) of orders 7, 5 and 3
+  if (s.dim == 2 && s.N == 8 && s.Np == 6)
+    rc = go(stokes_div_kernel<T, 2, 8, 6>);
+  else if (s.dim == 2 && s.N == 6 && s.Np == 4)
+    rc = go(stokes_div_kernel<T, 2, 6, 4>);
+  else if (s.dim == 2 && s.N == 4 && s.Np == 2)
+    rc = go(stokes_div_kernel<T, 2, 4, 2>);
+  else if (s.dim == 3 && s.N == 8 && s.Np == 6)
+    rc = go(stokes_div_kernel<T, 3, 8, 6>);
+  else
+    rc = go(stokes_div_kernel<T>);
+  if (rc) return rc;
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }
@@ -337,10 +378,27 @@ int stokes_grad_t_impl(const sfem_space* v, const sfem_space* p,
   int64_t blocks = (E + warps - 1) / warps;
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  stokes_grad_t_kernel<T><<<(unsigned)blocks, 32 * warps, smem, stream>>>(
-      s, tables_of<T>(v), tables_of<T>(p), v->base.desc.elements,
-      p->base.desc.elements, (const T*)v->invjacs, (const T*)v->jacdets,
-      (const T*)pr, (const T*)mask, E, slice, (T*)out);
+  auto go = [&](auto kernel) -> int {
+    if (smem > 48 * 1024)
+      SFEM_CUDA_CHECK(cudaFuncSetAttribute(
+          kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<(unsigned)blocks, 32 * warps, smem, stream>>>(
+        s, tables_of<T>(v), tables_of<T>(p), v->base.desc.elements,
+        p->base.desc.elements, (const T*)v->invjacs, (const T*)v->jacdets,
+        (const T*)pr, (const T*)mask, E, slice, (T*)out);
+    return SFEM_OK;
+  };
+  if (s.dim == 2 && s.N == 8 && s.Np == 6)
+    rc = go(stokes_grad_t_kernel<T, 2, 8, 6>);
+  else if (s.dim == 2 && s.N == 6 && s.Np == 4)
+    rc = go(stokes_grad_t_kernel<T, 2, 6, 4>);
+  else if (s.dim == 2 && s.N == 4 && s.Np == 2)
+    rc = go(stokes_grad_t_kernel<T, 2, 4, 2>);
+  else if (s.dim == 3 && s.N == 8 && s.Np == 6)
+    rc = go(stokes_grad_t_kernel<T, 3, 8, 6>);
+  else
+    rc = go(stokes_grad_t_kernel<T>);
+  if (rc) return rc;
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }

@@ -91,6 +91,11 @@ def _fused_cg(A: BoundOperator, b, x0, tol, atol, maxiter, M, check_every):
   return x, {'residual': residual, 'num_iterations': int(info.num_iterations)}
 
 
+# Diagnostics of the most recent `_device_state_cg` call (tools/bench_ns.py):
+# whether the iteration body was captured into a CUDA graph.
+LAST_DEVICE_STATE_RUN = {}
+
+
 def _device_state_cg(A, b, x0, tol, atol, maxiter, M, check_every,
                      graph=None):
   """cg.py:54-97 for callables `A`, `M` on one CUDA tensor, scalars on the
@@ -100,13 +105,16 @@ def _device_state_cg(A, b, x0, tol, atol, maxiter, M, check_every,
   set the vector kernels are no-ops, so the count equals the reference's.
 
   `graph` (default: env SFEM_CG_GRAPH, on): the iteration body -- whatever
-  kernels `A` and `M` launch plus the five above -- is captured ONCE into a
-  CUDA graph after a first eager iteration and replayed; the body is static
-  because every scalar lives in the device state.  For the launch-bound
-  Stokes solves (dozens of small kernels per iteration) this removes the
-  per-launch host cost.  Callables that cannot be captured (host
+  kernels `A` and `M` launch plus the five above -- may be captured into a
+  CUDA graph and replayed; the body is static because every scalar lives in
+  the device state.  It is captured only where that pays: after 4 *
+  `check_every` eager iterations, and only if the eager batches were
+  host-bound (launch-bound Stokes solves on small meshes: 222 -> 90 us per
+  pressure iteration at 147 k dofs; at 2.4 M dofs the eager loop is already
+  GPU-bound and stays eager).  Callables that cannot be captured (host
   synchronisation inside) fall back to eager launches."""
   import os  # pylint: disable=g-import-not-at-top
+  import time  # pylint: disable=g-import-not-at-top
   if graph is None:
     graph = os.environ.get('SFEM_CG_GRAPH', '1') != '0'
   lib = _lib.lib()
@@ -169,33 +177,77 @@ def _device_state_cg(A, b, x0, tol, atol, maxiter, M, check_every,
                   'sfem_cg_direction')
       _lib._check(lib.sfem_cg_advance(_lib.ptr(state), st), 'sfem_cg_advance')
 
+    def capture():
+      """The iteration body as a CUDA graph, or False if it cannot be captured.
+      (`CUDAGraph.capture_begin/_end` directly: the `torch.cuda.graph` context
+      also runs `gc.collect()` and `torch.cuda.empty_cache()`, which costs
+      ~1 s per solve once the caching allocator holds GBs -- measured on the
+      Stokes step at 3.2 M velocity dofs.)"""
+      cur = torch.cuda.current_stream(dev)
+      side = torch.cuda.Stream(device=dev)
+      side.wait_stream(cur)
+      g = torch.cuda.CUDAGraph()
+      ok = True
+      with torch.cuda.stream(side):
+        g.capture_begin()
+        try:
+          iteration()
+        except Exception:  # pylint: disable=broad-except
+          ok = False
+        try:
+          g.capture_end()
+        except Exception:  # pylint: disable=broad-except
+          ok = False
+      cur.wait_stream(side)
+      if not ok:
+        torch.cuda.synchronize(dev)
+        return False
+      return g
+
+    # Eager first: a graph pays off only when the HOST is the limit (many small
+    # kernels) and the solve is long.  Every eager batch is timed -- enqueue
+    # time against the time until the state read returns -- and the body is
+    # captured after `capture_after` eager iterations if the host needed most
+    # of the time of the last three batches to enqueue them.
+    capture_after = 4 * max(1, int(check_every))
     captured = None
     eager_done = 0
+    host_bound = False
+    streak = 0       # consecutive host-bound eager batches
+    pending = None   # (start, enqueue time) of the eager batch in flight
     while True:
       _lib._check(lib.sfem_cg_read(_lib.ptr(state), ctypes.byref(info),
                                    ctypes.byref(done), stream), 'sfem_cg_read')
+      if pending is not None:
+        total = time.perf_counter() - pending[0]
+        host_bound = pending[1] > 0.6 * total
+        streak = streak + 1 if host_bound else 0
+        pending = None
       if done.value:
         break
       iters = int(min(check_every, max(1, maxiter - info.num_iterations)))
-      if graph and captured is None and eager_done == 0:
-        iters = 1   # one eager iteration, then capture
-      if graph and captured is None and eager_done >= 1:
+      if (graph and captured is None and streak >= 3
+          and eager_done >= capture_after):
         # everything lazy (module loading, occupancy queries, cached index
-        # maxima) happened in the eager iteration(s): capture the body now
+        # maxima) happened in the eager iterations
         try:
-          g = torch.cuda.CUDAGraph()
-          with torch.cuda.graph(g):
-            iteration()
-          captured = g
+          captured = capture()
         except Exception:  # pylint: disable=broad-except
           captured = False   # not capturable: stay eager
           torch.cuda.synchronize(dev)
-      for _ in range(iters):
-        if captured:
+      if captured:
+        for _ in range(iters):
           captured.replay()
-        else:
+      else:
+        t0 = time.perf_counter()
+        for _ in range(iters):
           iteration()
-          eager_done += 1
+        eager_done += iters
+        pending = (t0, time.perf_counter() - t0)
+  LAST_DEVICE_STATE_RUN.update(
+      graph_requested=bool(graph), graph_captured=bool(captured),
+      host_bound=bool(host_bound), eager_iterations=eager_done,
+      iterations=int(info.num_iterations))
   residual = torch.tensor(info.residual, dtype=dtype, device=dev)
   return x, {'residual': residual, 'num_iterations': int(info.num_iterations)}
 

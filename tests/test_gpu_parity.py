@@ -1167,3 +1167,34 @@ def test_lazy_zero_fill_matches_eager(seed, dtype):
   out = torch.full_like(x, float('nan'))
   assert float((op.apply(x, lam=0.7, mu=1.3, out=out) - y_e).abs().max()) \
       <= eps * scale
+
+
+@pytest.mark.gpu
+def test_device_state_cg_graph_replay_matches_eager():
+  """`linalg.cg.cg` with callable `A` / `M` (device-state path): the iteration
+  body captured into a CUDA graph after the first eager batches (host-bound
+  small problem) gives the iteration count and solution of the eager loop."""
+  from swirl_fem_b200.linalg import cg as cgmod
+  # (shuffled element order only: re-oriented quads have det J < 0, and the
+  # operator would not be positive definite)
+  refined, mesh, space, oracle, bmask = _build(2, 6, 6, GLL, 6, torch.float64,
+                                               seed=11, reorient=False)
+  del oracle
+  op = space.operator(dirichlet_mask=bmask, with_mass=True)
+  dev = mesh.device
+  rhs = op.apply(torch.ones(mesh.num_nodes, dtype=torch.float64, device=dev),
+                 lam=1.0, mu=0.0)
+  d = op.diag(lam=1.0, mu=1.0)
+  minv = torch.where(d != 0, 1.0 / d, torch.zeros_like(d))
+  A = lambda v: op.apply(v, lam=1.0, mu=1.0)   # noqa: E731  (a plain callable)
+  M = lambda r: minv * r                        # noqa: E731
+  xe, ie = cgmod.cg(A, rhs, M=M, tol=1e-13, maxiter=400, graph=False,
+                    check_every=4)
+  assert not cgmod.LAST_DEVICE_STATE_RUN['graph_captured']
+  xg, ig = cgmod.cg(A, rhs, M=M, tol=1e-13, maxiter=400, graph=True,
+                    check_every=4)
+  run = dict(cgmod.LAST_DEVICE_STATE_RUN)
+  assert ie['num_iterations'] > 24, ie       # long enough to reach the capture
+  assert run['graph_captured'] and run['eager_iterations'] >= 16, run
+  assert ig['num_iterations'] == ie['num_iterations']
+  assert float((xg - xe).abs().max()) <= 1e-12 * float(xe.abs().max())
