@@ -130,13 +130,41 @@ stokes_div_kernel(StokesShape s_rt, const T* __restrict__ vtab,
   T* t0 = H + s.n;        // (n)
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  // fixed shapes: the connectivity of the NEXT element is fetched while this
+  // one is computed (one dependent global round trip less per element)
+  constexpr bool FIXED = DIM_ > 0;
+  constexpr int PASSES = FIXED ? (cpow_s(N_, DIM_) + 31) / 32 : 1;
+  int32_t gnext[PASSES];
+  auto fetch_conn = [&](int64_t e2) {
+#pragma unroll
+    for (int k = 0; k < PASSES; ++k) {
+      const int i = lane + 32 * k;
+      gnext[k] = (e2 < E && i < s.n) ? __ldg(v_el + e2 * s.n + i) : SFEM_SENTINEL;
+    }
+  };
+  if (FIXED) fetch_conn(warp);
   for (int64_t e = warp; e < E; e += nwarps) {
-    for (int i = lane; i < s.n; i += 32) {
-      const int32_t g = v_el[e * s.n + i];
-      for (int j = 0; j < d; ++j)
-        U[j * s.n + i] = g == SFEM_SENTINEL ? T(0) : u[(int64_t)g * d + j];
+    if constexpr (FIXED) {
+#pragma unroll
+      for (int k = 0; k < PASSES; ++k) {
+        const int i = lane + 32 * k;
+        const int32_t g = gnext[k];
+        if (i < s.n) {
+#pragma unroll
+          for (int j = 0; j < DIM_; ++j)
+            U[j * s.n + i] = g == SFEM_SENTINEL ? T(0) : u[(int64_t)g * d + j];
+        }
+      }
+      fetch_conn(e + nwarps);
+    } else {
+      for (int i = lane; i < s.n; i += 32) {
+        const int32_t g = v_el[e * s.n + i];
+        for (int j = 0; j < d; ++j)
+          U[j * s.n + i] = g == SFEM_SENTINEL ? T(0) : u[(int64_t)g * d + j];
+      }
     }
     __syncwarp();
+#pragma unroll
     for (int q = lane; q < s.n; q += 32) {
       const int64_t eq = e * s.n + q;
       const T* inv = invjacs + eq * d * d;
@@ -203,10 +231,31 @@ stokes_grad_t_kernel(StokesShape s_rt, const T* __restrict__ vtab,
   T* F = t0 + s.n;         // (d * d, n): F[a][k][q] = c_q Jinv[k][a]
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  constexpr bool FIXED = DIM_ > 0;
+  constexpr int PPASSES = FIXED ? (cpow_s(NP_, DIM_) + 31) / 32 : 1;
+  int32_t gnext[PPASSES];
+  auto fetch_conn = [&](int64_t e2) {
+#pragma unroll
+    for (int k = 0; k < PPASSES; ++k) {
+      const int m = lane + 32 * k;
+      gnext[k] = (e2 < E && m < s.np) ? __ldg(p_el + e2 * s.np + m) : SFEM_SENTINEL;
+    }
+  };
+  if (FIXED) fetch_conn(warp);
   for (int64_t e = warp; e < E; e += nwarps) {
-    for (int m = lane; m < s.np; m += 32) {
-      const int32_t g = p_el[e * s.np + m];
-      P[m] = g == SFEM_SENTINEL ? T(0) : p[g];
+    if constexpr (FIXED) {
+#pragma unroll
+      for (int k = 0; k < PPASSES; ++k) {
+        const int m = lane + 32 * k;
+        const int32_t g = gnext[k];
+        if (m < s.np) P[m] = g == SFEM_SENTINEL ? T(0) : p[g];
+      }
+      fetch_conn(e + nwarps);
+    } else {
+      for (int m = lane; m < s.np; m += 32) {
+        const int32_t g = p_el[e * s.np + m];
+        P[m] = g == SFEM_SENTINEL ? T(0) : p[g];
+      }
     }
     __syncwarp();
     // p(q) = sum_m Bp^{(x)}[q, m] P[m]: last axis first, Np -> N
@@ -221,6 +270,7 @@ stokes_grad_t_kernel(StokesShape s_rt, const T* __restrict__ vtab,
       in = o;
       which ^= 1;
     }
+#pragma unroll
     for (int q = lane; q < s.n; q += 32) {
       const int64_t eq = e * s.n + q;
       const T c = quad_w<T>(s, W, q) * jacdets[eq] * in[q];
@@ -292,6 +342,16 @@ int check_pair(const sfem_space* v, const sfem_space* p, StokesShape* s) {
   return SFEM_OK;
 }
 
+// Persistent CTAs (4 warps each) per SM; SFEM_STOKES_CTAS: developer switch.
+inline int stokes_ctas_per_sm() {
+  static const int v = [] {
+    const char* e = getenv("SFEM_STOKES_CTAS");
+    const int x = e ? atoi(e) : 0;
+    return x > 0 && x <= 16 ? x : 8;
+  }();
+  return v;
+}
+
 template <typename T, typename K>
 int launch_stokes(K kernel, const StokesShape& s, int slice_elems,
                   int64_t E, cudaStream_t stream, int* warps_out,
@@ -330,7 +390,7 @@ int stokes_div_impl(const sfem_space* v, const sfem_space* p, const void* u,
   rc = launch_stokes<T>(stokes_div_kernel<T>, s, slice, E, stream, &warps, &smem);
   if (rc) return rc;
   int64_t blocks = (E + warps - 1) / warps;
-  const int64_t cap = (int64_t)num_sms() * 8;
+  const int64_t cap = (int64_t)num_sms() * stokes_ctas_per_sm();
   if (blocks > cap) blocks = cap;
   auto go = [&](auto kernel) -> int {
     if (smem > 48 * 1024)
@@ -376,7 +436,7 @@ int stokes_grad_t_impl(const sfem_space* v, const sfem_space* p,
                         &smem);
   if (rc) return rc;
   int64_t blocks = (E + warps - 1) / warps;
-  const int64_t cap = (int64_t)num_sms() * 8;
+  const int64_t cap = (int64_t)num_sms() * stokes_ctas_per_sm();
   if (blocks > cap) blocks = cap;
   auto go = [&](auto kernel) -> int {
     if (smem > 48 * 1024)

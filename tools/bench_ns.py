@@ -29,6 +29,8 @@ def main():
   ap.add_argument('--order', type=int, default=7)
   ap.add_argument('--reps', type=int, default=20)
   ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'])
+  ap.add_argument('--ops-only', action='store_true',
+                  help='time the operators only (profiling runs)')
   args = ap.parse_args()
 
   import torch
@@ -92,6 +94,9 @@ def main():
     out['us'][name] = t
     if name in traffic:
       out['gbs'][name] = traffic[name] / (t * 1e-6) / 1e9
+  if args.ops_only:
+    print(json.dumps(out))
+    return
   us_hist = [u * (1.0 - 0.01 * i) for i in range(k)]
   ps_hist = [p * 0.0 for _ in range(k)]
   torch.cuda.synchronize()

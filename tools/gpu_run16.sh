@@ -1,22 +1,26 @@
 #!/usr/bin/env bash
-# Round-2 GPU job 16 (1 GPU): Stokes pieces -- specialised D / D^T kernels,
-# CG graph heuristic; tests, then the Stokes step at ne = 64 and 256.
+# Round-2 GPU job 16 (1 GPU): Stokes pieces -- specialised D / D^T kernels
+# with connectivity prefetch, occupancy variants; tests, then the Stokes step.
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
 timeout 600 python -m pytest tests/test_navier_stokes_gpu.py tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider --tb=short -k "navier or stokes or fused_div or kolmogorov or graph_replay or device_state" > $O/r2_run16_pytest.log 2>&1
-tail -5 $O/r2_run16_pytest.log
-for ne in 64 256; do
-timeout 400 python tools/bench_ns.py --ne $ne --order 7 --reps 10 > $O/r2_bench_ns_ne${ne}_detail.json 2> $O/r2_bench_ns_ne${ne}_detail.err
-tail -3 $O/r2_bench_ns_ne${ne}_detail.err
-python - $ne <<'PY'
+tail -3 $O/r2_run16_pytest.log
+for ctas in 8 12 16; do
+for ne in 256; do
+SFEM_STOKES_CTAS=$ctas timeout 400 python tools/bench_ns.py --ne $ne --order 7 --reps 10 > $O/r2_bench_ns_ne${ne}_ctas${ctas}.json 2> $O/r2_bench_ns_ne${ne}_ctas${ctas}.err
+tail -3 $O/r2_bench_ns_ne${ne}_ctas${ctas}.err
+python - $ne $ctas <<'PY'
 import json, sys
-d = json.loads(open(f'gpurun_out/r2_bench_ns_ne{sys.argv[1]}_detail.json').read().strip().splitlines()[-1])
-print({k: round(v, 1) for k, v in d['us'].items()})
-print({k: round(v, 1) for k, v in d['gbs'].items()})
-for k, v in d.items():
-  if k not in ('us', 'gbs'):
-    print(k, v)
+d = json.loads(open(f'gpurun_out/r2_bench_ns_ne{sys.argv[1]}_ctas{sys.argv[2]}.json').read().strip().splitlines()[-1])
+print('ctas', sys.argv[2], {k: round(v, 1) for k, v in d['us'].items()}, 'step', round(d['stokes_one_step_ms']), round(d['stokes_one_step_second_call_ms']), d['dp_iterations'])
 PY
 done
+done
+SFEM_STOKES_CTAS=8 timeout 400 python tools/bench_ns.py --ne 64 --order 7 --reps 10 > $O/r2_bench_ns_ne64_detail.json 2> $O/r2_bench_ns_ne64_detail.err
+python - <<'PY'
+import json, sys
+d = json.loads(open(f'gpurun_out/r2_bench_ns_ne64_detail.json').read().strip().splitlines()[-1])
+print('ne64', {k: round(v, 1) for k, v in d['us'].items()}, 'step', round(d['stokes_one_step_ms']), round(d['stokes_one_step_second_call_ms']), d['dp_iterations'])
+PY
 echo done
