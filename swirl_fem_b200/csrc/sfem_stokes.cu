@@ -307,6 +307,307 @@ stokes_grad_t_kernel(StokesShape s_rt, const T* __restrict__ vtab,
   }
 }
 
+
+// ---- 2-D, compile-time (N, NP): one lane per LINE ------------------------------
+// ncu on the kernels above (profiles/r02_ncu_stokes_div_ne256.txt): shared-
+// memory bound -- 401 / 278 wavefronts per element, MIO-throttle and short-
+// scoreboard stalls of 9 cycles per issue -- because every POINT re-loads its
+// 8 line values and 8 matrix entries for each derivative.  Here a lane owns a
+// whole line (row or column) of one field: N loads feed N outputs (N^2 FMAs
+// from registers), the 1-D matrices are kernel parameters (constant bank: FMA
+// operands, no load instruction), tiles have a row pitch of N + 1 so that rows
+// and columns are both conflict-free, and the connectivity of the next
+// element is prefetched.  ~95 wavefronts per element.
+template <typename T, int N, int NP>
+struct StokesTabs {
+  T Dv[N * N];   // Dv[q * N + m]  = d phi_m / d xi (xi_q)
+  T Bp[N * NP];  // Bp[q * NP + m] = psi_m (xi_q)
+  T W[N];
+};
+
+template <typename T, int N, int NP>
+StokesTabs<T, N, NP> make_stokes_tabs(const sfem_space* v, const sfem_space* p) {
+  StokesTabs<T, N, NP> tb;
+  for (int i = 0; i < N * N; ++i) tb.Dv[i] = (T)v->base.h_BD[i];
+  for (int i = 0; i < N * NP; ++i) tb.Bp[i] = (T)p->base.h_B[i];
+  for (int i = 0; i < N; ++i) tb.W[i] = (T)v->base.h_W[i];
+  return tb;
+}
+
+template <typename T, int N, int NP>
+__global__ void __launch_bounds__(32 * kStokesMaxWarps)
+stokes_div2d_kernel(const __grid_constant__ StokesTabs<T, N, NP> tb,
+                    const int32_t* __restrict__ v_el,
+                    const int32_t* __restrict__ p_el,
+                    const T* __restrict__ invjacs,
+                    const T* __restrict__ jacdets, const T* __restrict__ u,
+                    int64_t E, T* __restrict__ out) {
+  constexpr int n = N * N, np = NP * NP, R = N + 1, tile = N * R;
+  constexpr int PASSES = (n + 31) / 32, PPASSES = (np + 31) / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  T* mine = reinterpret_cast<T*>(smem_raw) + (size_t)(threadIdx.x >> 5) * (6 * tile);
+  T* U = mine;             // [2][tile]; U[0] becomes H, U[1] the half-contracted T1
+  T* G = mine + 2 * tile;  // [j * 2 + a][tile]
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int32_t gnext[PASSES], pnext[PPASSES];
+  auto fetch_conn = [&](int64_t e2) {
+#pragma unroll
+    for (int k = 0; k < PASSES; ++k) {
+      const int i = lane + 32 * k;
+      gnext[k] = (e2 < E && i < n) ? __ldg(v_el + e2 * n + i) : SFEM_SENTINEL;
+    }
+#pragma unroll
+    for (int k = 0; k < PPASSES; ++k) {
+      const int m = lane + 32 * k;
+      pnext[k] = (e2 < E && m < np) ? __ldg(p_el + e2 * np + m) : SFEM_SENTINEL;
+    }
+  };
+  fetch_conn(warp);
+  for (int64_t e = warp; e < E; e += nwarps) {
+    int32_t pg[PPASSES];
+#pragma unroll
+    for (int k = 0; k < PPASSES; ++k) pg[k] = pnext[k];
+#pragma unroll
+    for (int k = 0; k < PASSES; ++k) {
+      const int i = lane + 32 * k;
+      if (i < n) {
+        const int32_t g = gnext[k];
+        const int at = (i / N) * R + (i % N);
+        U[at] = g == SFEM_SENTINEL ? T(0) : u[(int64_t)g * 2];
+        U[tile + at] = g == SFEM_SENTINEL ? T(0) : u[(int64_t)g * 2 + 1];
+      }
+    }
+    fetch_conn(e + nwarps);
+    // the geometric data of this element's points (used after the derivatives)
+    T inv[PASSES][4], jd[PASSES];
+#pragma unroll
+    for (int k = 0; k < PASSES; ++k) {
+      const int q = lane + 32 * k;
+      if (q < n) {
+        const int64_t eq = e * n + q;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) inv[k][c] = invjacs[eq * 4 + c];
+        jd[k] = jacdets[eq];
+      }
+    }
+    __syncwarp();
+    // line derivatives: task (a, j, l); a = 1: row l (fastest index), a = 0:
+    // column l.  (a is the slowest task index: for N = 8 a half-warp then reads
+    // 16 columns -- or 16 rows -- of two tiles 8 bank pairs apart: no conflicts.)
+    for (int t = lane; t < 4 * N; t += 32) {
+      const int l = t % N, j = (t / N) & 1, a = t / (2 * N);
+      const int st = a ? 1 : R;
+      const int first = a ? l * R : l;
+      const T* src = U + j * tile + first;
+      T v[N];
+#pragma unroll
+      for (int m = 0; m < N; ++m) v[m] = src[m * st];
+      T* dst = G + (j * 2 + a) * tile + first;
+#pragma unroll
+      for (int o = 0; o < N; ++o) {
+        T acc = T(0);
+#pragma unroll
+        for (int m = 0; m < N; ++m) acc += tb.Dv[o * N + m] * v[m];
+        dst[o * st] = acc;
+      }
+    }
+    __syncwarp();
+    // weighted divergence at the points -> H (= U[0])
+#pragma unroll
+    for (int k = 0; k < PASSES; ++k) {
+      const int q = lane + 32 * k;
+      if (q < n) {
+        const int r = q / N, c = q % N, at = r * R + c;
+        T div = T(0);
+#pragma unroll
+        for (int ja = 0; ja < 4; ++ja) div += G[ja * tile + at] * inv[k][ja];
+        U[at] = tb.W[r] * tb.W[c] * jd[k] * div;
+      }
+    }
+    __syncwarp();
+    // pressure basis, axis 0: one lane per column c: T1[m0][c] = sum_q0 Bp[q0][m0] H[q0][c]
+    if (lane < N) {
+      T h[N];
+#pragma unroll
+      for (int q0 = 0; q0 < N; ++q0) h[q0] = U[q0 * R + lane];
+#pragma unroll
+      for (int m0 = 0; m0 < NP; ++m0) {
+        T acc = T(0);
+#pragma unroll
+        for (int q0 = 0; q0 < N; ++q0) acc += tb.Bp[q0 * NP + m0] * h[q0];
+        U[tile + m0 * R + lane] = acc;
+      }
+    }
+    __syncwarp();
+    // axis 1: one lane per row m0: y[m0][m1] = sum_q1 Bp[q1][m1] T1[m0][q1]  -> G[0] (contiguous m)
+    if (lane < NP) {
+      T h[N];
+#pragma unroll
+      for (int q1 = 0; q1 < N; ++q1) h[q1] = U[tile + lane * R + q1];
+#pragma unroll
+      for (int m1 = 0; m1 < NP; ++m1) {
+        T acc = T(0);
+#pragma unroll
+        for (int q1 = 0; q1 < N; ++q1) acc += tb.Bp[q1 * NP + m1] * h[q1];
+        G[lane * NP + m1] = acc;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < PPASSES; ++k) {
+      const int m = lane + 32 * k;
+      if (m < np && pg[k] != SFEM_SENTINEL) red_add(out + pg[k], G[m]);
+    }
+    __syncwarp();
+  }
+}
+
+template <typename T, int N, int NP>
+__global__ void __launch_bounds__(32 * kStokesMaxWarps)
+stokes_grad_t2d_kernel(const __grid_constant__ StokesTabs<T, N, NP> tb,
+                       const int32_t* __restrict__ v_el,
+                       const int32_t* __restrict__ p_el,
+                       const T* __restrict__ invjacs,
+                       const T* __restrict__ jacdets, const T* __restrict__ p,
+                       const T* __restrict__ mask, int64_t E,
+                       T* __restrict__ out) {
+  constexpr int n = N * N, np = NP * NP, R = N + 1, tile = N * R;
+  constexpr int PASSES = (n + 31) / 32, PPASSES = (np + 31) / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  T* mine = reinterpret_cast<T*>(smem_raw) + (size_t)(threadIdx.x >> 5) * (6 * tile);
+  T* P = mine;             // [NP][R] pressure nodes, later V[N][R] values at the points
+  T* T1 = mine + tile;     // [NP][R]
+  T* F = mine + 2 * tile;  // [a * 2 + k][tile]
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int32_t gnext[PASSES], pnext[PPASSES];
+  auto fetch_conn = [&](int64_t e2) {
+#pragma unroll
+    for (int k = 0; k < PASSES; ++k) {
+      const int i = lane + 32 * k;
+      gnext[k] = (e2 < E && i < n) ? __ldg(v_el + e2 * n + i) : SFEM_SENTINEL;
+    }
+#pragma unroll
+    for (int k = 0; k < PPASSES; ++k) {
+      const int m = lane + 32 * k;
+      pnext[k] = (e2 < E && m < np) ? __ldg(p_el + e2 * np + m) : SFEM_SENTINEL;
+    }
+  };
+  fetch_conn(warp);
+  for (int64_t e = warp; e < E; e += nwarps) {
+    int32_t vg[PASSES];
+#pragma unroll
+    for (int k = 0; k < PASSES; ++k) vg[k] = gnext[k];
+#pragma unroll
+    for (int k = 0; k < PPASSES; ++k) {
+      const int m = lane + 32 * k;
+      if (m < np) {
+        const int32_t g = pnext[k];
+        P[(m / NP) * R + (m % NP)] = g == SFEM_SENTINEL ? T(0) : p[g];
+      }
+    }
+    fetch_conn(e + nwarps);
+    T inv[PASSES][4], jd[PASSES], w[PASSES];
+#pragma unroll
+    for (int k = 0; k < PASSES; ++k) {
+      const int q = lane + 32 * k;
+      w[k] = T(0);
+      if (q < n) {
+        const int64_t eq = e * n + q;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) inv[k][c] = invjacs[eq * 4 + c];
+        jd[k] = jacdets[eq];
+        if (vg[k] != SFEM_SENTINEL) w[k] = mask ? mask[vg[k]] : T(1);
+      }
+    }
+    __syncwarp();
+    // interpolation, axis 1: one lane per row m0: T1[m0][q1] = sum_m1 Bp[q1][m1] P[m0][m1]
+    if (lane < NP) {
+      T h[NP];
+#pragma unroll
+      for (int m1 = 0; m1 < NP; ++m1) h[m1] = P[lane * R + m1];
+#pragma unroll
+      for (int q1 = 0; q1 < N; ++q1) {
+        T acc = T(0);
+#pragma unroll
+        for (int m1 = 0; m1 < NP; ++m1) acc += tb.Bp[q1 * NP + m1] * h[m1];
+        T1[lane * R + q1] = acc;
+      }
+    }
+    __syncwarp();
+    // axis 0: one lane per column q1: V[q0][q1] = sum_m0 Bp[q0][m0] T1[m0][q1]  -> P
+    if (lane < N) {
+      T h[NP];
+#pragma unroll
+      for (int m0 = 0; m0 < NP; ++m0) h[m0] = T1[m0 * R + lane];
+#pragma unroll
+      for (int q0 = 0; q0 < N; ++q0) {
+        T acc = T(0);
+#pragma unroll
+        for (int m0 = 0; m0 < NP; ++m0) acc += tb.Bp[q0 * NP + m0] * h[m0];
+        P[q0 * R + lane] = acc;
+      }
+    }
+    __syncwarp();
+    // F[a][k][q] = W_q detJ_q p(q) Jinv[k][a]
+#pragma unroll
+    for (int kk = 0; kk < PASSES; ++kk) {
+      const int q = lane + 32 * kk;
+      if (q < n) {
+        const int r = q / N, c = q % N, at = r * R + c;
+        const T cq = tb.W[r] * tb.W[c] * jd[kk] * P[at];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            F[(a * 2 + k) * tile + at] = cq * inv[kk][k * 2 + a];
+      }
+    }
+    __syncwarp();
+    // transposed derivative along every line, in place: task (a, k, l)
+    for (int t = lane; t < 4 * N; t += 32) {
+      const int l = t % N, k = (t / N) & 1, a = t / (2 * N);
+      const int st = a ? 1 : R;
+      T* line = F + (a * 2 + k) * tile + (a ? l * R : l);
+      T f[N];
+#pragma unroll
+      for (int m = 0; m < N; ++m) f[m] = line[m * st];
+#pragma unroll
+      for (int o = 0; o < N; ++o) {
+        T acc = T(0);
+#pragma unroll
+        for (int m = 0; m < N; ++m) acc += tb.Dv[m * N + o] * f[m];
+        line[o * st] = acc;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int kk = 0; kk < PASSES; ++kk) {
+      const int i = lane + 32 * kk;
+      if (i < n && vg[kk] != SFEM_SENTINEL) {
+        const int at = (i / N) * R + (i % N);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          red_add(out + (int64_t)vg[kk] * 2 + k,
+                  w[kk] * (F[k * tile + at] + F[(2 + k) * tile + at]));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// SFEM_STOKES_LINES=0 (developer switch): the point-per-lane kernels instead.
+inline bool stokes_lines_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SFEM_STOKES_LINES");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 template <typename T>
 const T* tables_of(const sfem_space* sp);
 template <>
@@ -402,8 +703,25 @@ int stokes_div_impl(const sfem_space* v, const sfem_space* p, const void* u,
         (const T*)u, E, slice, (T*)out);
     return SFEM_OK;
   };
-  // specialised shapes: the Stokes pairs (N, N - 2) of orders 7, 5 and 3
-  if (s.dim == 2 && s.N == 8 && s.Np == 6)
+  // 2-D Stokes pairs (N, N - 2) of orders 7, 5 and 3: one lane per line
+  auto go2d = [&](auto kernel, auto tabs) -> int {
+    constexpr int n1 = sizeof(tabs.W) / sizeof(T);
+    const size_t bytes = (size_t)4 * 6 * n1 * (n1 + 1) * sizeof(T);
+    int64_t b2 = (E + 3) / 4;
+    if (b2 > cap) b2 = cap;
+    kernel<<<(unsigned)b2, 128, bytes, stream>>>(
+        tabs, v->base.desc.elements, p->base.desc.elements,
+        (const T*)v->invjacs, (const T*)v->jacdets, (const T*)u, E, (T*)out);
+    return SFEM_OK;
+  };
+  if (s.dim == 2 && stokes_lines_enabled() && s.N == 8 && s.Np == 6)
+    rc = go2d(stokes_div2d_kernel<T, 8, 6>, make_stokes_tabs<T, 8, 6>(v, p));
+  else if (s.dim == 2 && stokes_lines_enabled() && s.N == 6 && s.Np == 4)
+    rc = go2d(stokes_div2d_kernel<T, 6, 4>, make_stokes_tabs<T, 6, 4>(v, p));
+  else if (s.dim == 2 && stokes_lines_enabled() && s.N == 4 && s.Np == 2)
+    rc = go2d(stokes_div2d_kernel<T, 4, 2>, make_stokes_tabs<T, 4, 2>(v, p));
+  // specialised shapes of the point-per-lane kernel
+  else if (s.dim == 2 && s.N == 8 && s.Np == 6)
     rc = go(stokes_div_kernel<T, 2, 8, 6>);
   else if (s.dim == 2 && s.N == 6 && s.Np == 4)
     rc = go(stokes_div_kernel<T, 2, 6, 4>);
@@ -448,7 +766,24 @@ int stokes_grad_t_impl(const sfem_space* v, const sfem_space* p,
         (const T*)pr, (const T*)mask, E, slice, (T*)out);
     return SFEM_OK;
   };
-  if (s.dim == 2 && s.N == 8 && s.Np == 6)
+  auto go2d = [&](auto kernel, auto tabs) -> int {
+    constexpr int n1 = sizeof(tabs.W) / sizeof(T);
+    const size_t bytes = (size_t)4 * 6 * n1 * (n1 + 1) * sizeof(T);
+    int64_t b2 = (E + 3) / 4;
+    if (b2 > cap) b2 = cap;
+    kernel<<<(unsigned)b2, 128, bytes, stream>>>(
+        tabs, v->base.desc.elements, p->base.desc.elements,
+        (const T*)v->invjacs, (const T*)v->jacdets, (const T*)pr,
+        (const T*)mask, E, (T*)out);
+    return SFEM_OK;
+  };
+  if (s.dim == 2 && stokes_lines_enabled() && s.N == 8 && s.Np == 6)
+    rc = go2d(stokes_grad_t2d_kernel<T, 8, 6>, make_stokes_tabs<T, 8, 6>(v, p));
+  else if (s.dim == 2 && stokes_lines_enabled() && s.N == 6 && s.Np == 4)
+    rc = go2d(stokes_grad_t2d_kernel<T, 6, 4>, make_stokes_tabs<T, 6, 4>(v, p));
+  else if (s.dim == 2 && stokes_lines_enabled() && s.N == 4 && s.Np == 2)
+    rc = go2d(stokes_grad_t2d_kernel<T, 4, 2>, make_stokes_tabs<T, 4, 2>(v, p));
+  else if (s.dim == 2 && s.N == 8 && s.Np == 6)
     rc = go(stokes_grad_t_kernel<T, 2, 8, 6>);
   else if (s.dim == 2 && s.N == 6 && s.Np == 4)
     rc = go(stokes_grad_t_kernel<T, 2, 6, 4>);
