@@ -424,7 +424,8 @@ def run_ours(args):
     # the apply kernel); SFEM_HALO=nccl keeps the pack / all_to_all / unpack
     # path for comparison
     if os.environ.get('SFEM_HALO', 'p2p') == 'p2p':
-      halo_path = ('peer memory (in-kernel NVLink push)'
+      halo_path = ('peer memory (NVLink stores from the companion kernel '
+                   'that runs next to the apply)'
                    if halo.enable_p2p(dtype, device) else
                    'nccl all_to_all (peer mapping failed)')
       # where the canonical sum runs: 1 in the apply kernel's own CTAs, 2 in
@@ -687,9 +688,9 @@ def run_ours(args):
                'launches_per_iteration': 2 if world == 1 else 3,
                'driver': 'sfem_cg (apply + one fused step kernel per '
                          'iteration)' if world == 1 else
-                         'distributed_cg -> sfem_cg_iterate (apply with '
-                         'in-kernel halo push, wait kernel, fused step kernel '
-                         'with the scalar all-reduces over peer memory)'
+                         'distributed_cg -> sfem_cg_iterate (apply, '
+                         'companion exchange kernel next to it, fused step '
+                         'kernel with the scalar all-reduces over peer memory)'
                          if halo_path and halo_path.startswith('peer') else
                          'distributed_cg (building blocks + NCCL scalars)'}
 

@@ -4,12 +4,13 @@ Same recurrence and stopping rule as `swirl_fem/linalg/cg.py:54-97` on a
 device-resident state.  Default path (peer-memory halo + `ScalarExchange`),
 THREE launches per iteration and rank, no NCCL call (`sfem_cg_iterate`):
 
-  apply kernel     local block, interface elements first, shared dofs pushed
-                   to the peers over NVLink from inside the kernel, canonical
-                   sum hidden under the interior elements, partial p.Ap in the
-                   epilogue (element-wise partial sums need no ownership
-                   weights)
-  wait kernel      whatever is left of the exchange (normally nothing)
+  apply kernel     local block, interface elements first (its CTAs signal
+                   when they are through them), partial p.Ap in the epilogue
+                   (element-wise partial sums need no ownership weights)
+  companion kernel runs NEXT to the apply in the warp slots it leaves free
+                   (`sfem_halo_wait_unpack`, exchange mode 3): pushes the
+                   shared dofs to the peers over NVLink, waits for theirs,
+                   canonical sum -- all under the interior elements
   step kernel      all-reduce of p.Ap over peer memory (warp 0 of CTA 0),
                    x, r update with partial r.z over the OWNED dofs, grid
                    arrival, all-reduce of r.z (last CTA), scalar advance +
