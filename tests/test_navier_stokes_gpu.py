@@ -311,8 +311,11 @@ def test_fixed_form_kernels_equal_the_general_form_path():
     assert rel_err(fast, general.cpu().numpy()) < 1e-13
 
 
+# (orders 7, 5, 3 in 2-D and 7 in 3-D have compile-time kernel instances -- in
+# 2-D the line-per-lane kernels --, the other cases take the runtime shapes)
 @pytest.mark.parametrize('ndim,ne,order', [(2, 5, 7), (2, 3, 4), (3, 2, 4),
-                                           (3, 2, 6)])
+                                           (3, 2, 6), (2, 4, 5), (2, 4, 3),
+                                           (3, 2, 7)])
 def test_fused_div_and_gradient_match_composed(ndim, ne, order):
   """`sfem_stokes_div` / `sfem_stokes_grad_t` (one launch each) against the
   composed element-local formulation (evaluation -> pointwise -> transposed
