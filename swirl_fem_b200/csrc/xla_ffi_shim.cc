@@ -243,4 +243,43 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(sfem_xla_cg, CgImpl,
                                   .Attr<double>("lam")
                                   .Attr<double>("mu"));
 
+// StokesSEM.D / Dt (swirl_fem/navier_stokes/navier_stokes.py:313-338) as ONE
+// launch each; `vspace` / `pspace` = addresses of the sfem_space handles of the
+// velocity and pressure spaces, created once outside jit.
+static ffi::Error StokesDivImpl(cudaStream_t stream, ffi::AnyBuffer u,
+                                ffi::Result<ffi::AnyBuffer> out, int64_t vspace,
+                                int64_t pspace) {
+  return Status(sfem_stokes_div(reinterpret_cast<const sfem_space*>(vspace),
+                                reinterpret_cast<const sfem_space*>(pspace),
+                                u.untyped_data(), out->untyped_data(),
+                                (sfem_stream_t)stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(sfem_xla_stokes_div, StokesDivImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<int64_t>("vspace")
+                                  .Attr<int64_t>("pspace"));
+
+// `mask`: the velocity interior mask (G_v,), or a zero-sized operand for none.
+static ffi::Error StokesGradTImpl(cudaStream_t stream, ffi::AnyBuffer p,
+                                  ffi::AnyBuffer mask,
+                                  ffi::Result<ffi::AnyBuffer> out,
+                                  int64_t vspace, int64_t pspace) {
+  return Status(sfem_stokes_grad_t(
+      reinterpret_cast<const sfem_space*>(vspace),
+      reinterpret_cast<const sfem_space*>(pspace), p.untyped_data(),
+      mask.element_count() ? mask.untyped_data() : nullptr,
+      out->untyped_data(), (sfem_stream_t)stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(sfem_xla_stokes_grad_t, StokesGradTImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<int64_t>("vspace")
+                                  .Attr<int64_t>("pspace"));
+
 #endif  // __has_include("xla/ffi/api/ffi.h")

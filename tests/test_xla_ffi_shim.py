@@ -24,7 +24,7 @@ CUDA_INC = '/usr/local/cuda/include'
 HANDLERS = ['sfem_xla_gather', 'sfem_xla_scatter_add', 'sfem_xla_op_apply',
             'sfem_xla_op_apply_local', 'sfem_xla_op_apply_halo',
             'sfem_xla_space_eval_transpose', 'sfem_xla_exchange',
-            'sfem_xla_cg']
+            'sfem_xla_cg', 'sfem_xla_stokes_div', 'sfem_xla_stokes_grad_t']
 
 
 def _need_toolchain():
